@@ -1,0 +1,124 @@
+/* mfgp.h -- C-ABI of libmfgp.so: the B200 (sm_100a) implementation of the Kennedy-O'Hagan
+ * linear multi-fidelity GP objective, its gradient and its predictive equations.
+ *
+ * Drop-in boundary.  The reference (qezlou/multi_fidelity_gpflow, pure Python) reaches
+ * this arithmetic through GPflow's operator API; each entry point below names the
+ * reference interface it replaces (file:line in /root/reference).  INTEGRATION.md shows
+ * the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - All matrices are dense, row-major, float64.  `X` arrays are [N, d+1] with the
+ *    fidelity indicator (exactly 0.0 or 1.0) in the last column (linear.py:67-70); rows
+ *    with any other fidelity value have all-zero covariance (linear.py:82,99-102).
+ *  - theta (per kernel) = [rho, ls_L[0..d-1], var_L, ls_delta[0..d-1], var_delta],
+ *    length 2d+3, CONSTRAINED values (the softplus chain rule lives in the host shim).
+ *  - Every pointer argument may be a HOST pointer or a DEVICE pointer of the handle's
+ *    device; the library detects which (cudaPointerGetAttributes) and stages host
+ *    buffers through the handle's stream.  Caller owns all buffers.
+ *  - Return value: 0 ok; >0 = LAPACK-style info (1-based index of the first non-positive
+ *    Cholesky pivot; for batched calls the first failing problem's info, per-problem
+ *    values in `info[]`); <0 = bad argument (-1), CUDA error (-2), not supported (-3).
+ *    mfgp_last_error() returns the message.
+ *  - A handle is not thread-safe: one handle per GPU per thread.  Calls are ordered on
+ *    the handle's stream and, unless async mode is on, synchronous on return.
+ */
+#ifndef MFGP_H
+#define MFGP_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mfgp_handle mfgp_handle;
+
+/* ---- lifetime / control ------------------------------------------------------------ */
+int mfgp_version(void);
+int mfgp_create(int device, mfgp_handle** out);
+int mfgp_destroy(mfgp_handle* h);
+/* Run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL = handle's own. */
+int mfgp_set_stream(mfgp_handle* h, void* cuda_stream);
+/* async != 0: calls whose outputs are all device pointers return without synchronising;
+ * non-PD status is then collected by mfgp_sync(). */
+int mfgp_set_async(mfgp_handle* h, int async);
+int mfgp_sync(mfgp_handle* h, int* info_out);
+const char* mfgp_last_error(mfgp_handle* h);
+int mfgp_sm_count(mfgp_handle* h);
+
+/* ---- K1: covariance assembly ---------------------------------------------------------
+ * replaces LinearMultiFidelityKernel.K (mfgpflow/linear.py:55-104) and K_diag (:106-136)
+ * X2 == NULL -> X2 = X (linear.py:59-60): the symmetric fast path computes the lower
+ * triangle of tiles once and mirrors it.  K is [N, N2] with leading dimension ldk. */
+int mfgp_cov(mfgp_handle* h, const double* X, int N, const double* X2, int N2, int d,
+             const double* theta, double* K, long ldk);
+int mfgp_cov_diag(mfgp_handle* h, const double* X, int N, int d, const double* theta, double* out);
+
+/* ---- K2..K5: exact multi-fidelity GPR -------------------------------------------------
+ * replaces gpflow GPR.log_marginal_likelihood as called at linear.py:206,227 (model built
+ * at linear.py:148-156: zero mean, Gaussian noise `noise`, ONE kernel/Cholesky shared by
+ * all P columns of Y [N, P]).  *nlml = -log_marginal_likelihood. */
+int mfgp_gpr_nlml(mfgp_handle* h, const double* X, const double* Y, int N, int d, int P,
+                  const double* theta, double noise, double* nlml);
+/* + analytic gradient of nlml w.r.t. [theta (2d+3), noise] -- replaces
+ * tape.gradient(loss, trainable_variables) at linear.py:207 (constrained space). */
+int mfgp_gpr_nlml_grad(mfgp_handle* h, const double* X, const double* Y, int N, int d, int P,
+                       const double* theta, double noise, double* nlml, double* grad /* [2d+4] */);
+/* replaces gpflow GPR.predict_f(Xnew) (tests/test_ho2021_multibin.py:83, tests/test_scipy.py:48):
+ * mean [Ns, P], var [Ns] (identical for every output column). */
+int mfgp_gpr_predict(mfgp_handle* h, const double* X, const double* Y, int N, int d, int P,
+                     const double* Xs, int Ns, const double* theta, double noise,
+                     double* mean, double* var);
+/* K6: "one GP per k-bin" (gpemulator_singlebin.py:1-14 design; BASELINE config 2): problem
+ * b uses y = Y[:, b] (Y is [N, B] row-major with leading dimension ldy), theta[b, :],
+ * noise[b].  nlml [B]; grad [B, 2d+4] or NULL; info [B] (int) or NULL.
+ * N <= 64 runs one CTA per problem entirely in shared memory. */
+int mfgp_gpr_batched_nlml_grad(mfgp_handle* h, const double* X, int N, int d, const double* Y,
+                               long ldy, int B, const double* theta, const double* noise,
+                               double* nlml, double* grad, int* info);
+
+/* ---- K7/K8: sparse variational GP (whitened, shared inducing points) -------------------
+ * replaces gpflow SVGP.elbo / prior_kl / predict_f as called at singlebin_svgp.py:83,97 and
+ * linear_svgp.py:177,184,188,199 with kernels SeparateIndependent (W == NULL, L == P,
+ * singlebin_svgp.py:39-47) or LinearCoregionalization (W [P, L], linear_svgp.py:121-122). */
+typedef struct {
+    int L;          /* latent GPs */
+    int M;          /* inducing points */
+    int P;          /* outputs */
+    int B;          /* rows in this (mini)batch */
+    int d;          /* input dimension without the fidelity column */
+    int hetero;     /* 1: Y is [B, 2P] = [Y_obs | Y_unc], var_eff = lik_var + Y_unc^2 (linear_svgp.py:259) */
+    double scale;   /* num_data / B, or 1 (singlebin_svgp.py passes no num_data) */
+    double kl_mult; /* loss = -ELBO + (kl_mult - 1) KL   (linear_svgp.py:188) */
+    double jitter;  /* gpflow default_jitter() = 1e-6 */
+} mfgp_svgp_cfg;
+
+/* Forward + hand-derived backward.  Outputs (any grad pointer may be NULL to skip all
+ * gradients): elbo, kl (scalars); gradients of loss w.r.t. CONSTRAINED values:
+ * gZ [M, d+1] (fidelity column == 0, quirk Q5), gtheta [L, 2d+3], gW [P, L] (NULL if W is
+ * NULL), gqmu [M, L], gqsqrt [L, M, M] (lower triangle, rest 0), glik (scalar). */
+int mfgp_svgp_elbo_grad(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* X, const double* Y,
+                        const double* Z, const double* theta, const double* W, const double* q_mu,
+                        const double* q_sqrt, double lik_var, double* elbo, double* kl,
+                        double* gZ, double* gtheta, double* gW, double* gqmu, double* gqsqrt,
+                        double* glik);
+/* mean [Ns, P], var [Ns, P]  (cfg->B is ignored, Ns rows are predicted). */
+int mfgp_svgp_predict(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* Xs, int Ns,
+                      const double* Z, const double* theta, const double* W, const double* q_mu,
+                      const double* q_sqrt, double* mean, double* var);
+
+/* ---- dense fp64 building blocks (exported for tests / bench / comparators) ------------- */
+/* C[m,n] = alpha * op(A) op(B) + beta * C, row-major; transa/transb are 'N' or 'T'.
+ * Runs the DMMA (mma.sync m8n8k4 f64) tile kernel. */
+int mfgp_gemm(mfgp_handle* h, char transa, char transb, int m, int n, int k, double alpha,
+              const double* A, long lda, const double* B, long ldb, double beta, double* C, long ldc);
+/* In-place lower Cholesky A = L L^T (row-major, strictly-upper part zeroed on return). */
+int mfgp_potrf(mfgp_handle* h, double* A, int N, long lda);
+/* Winv [N, N] = inv(L) for the lower factor produced by mfgp_potrf. */
+int mfgp_potrf_inv(mfgp_handle* h, double* A, int N, long lda, double* Winv, long ldw);
+/* FP64 pipe microbenchmarks (bench.py: measured FP64 peak).  kind 0: DFMA, 1: DMMA m8n8k4.
+ * Returns achieved FLOP/s in *flops. */
+int mfgp_fp64_peak(mfgp_handle* h, int kind, int iters, double* flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFGP_H */

@@ -1,0 +1,294 @@
+"""ctypes binding of libmfgp.so (C-ABI declared in include/mfgp.h).
+
+There is NO CPU fallback: importing this module without the built library raises, and
+creating a handle without a CUDA device raises.  Buffers may be NumPy arrays (host
+pointers; the library stages them through its stream) or CUDA tensors / any object with
+``data_ptr()`` or ``__cuda_array_interface__`` (device pointers, zero-copy).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmfgp.so")
+
+
+class MFGPError(RuntimeError):
+    pass
+
+
+class NotPositiveDefiniteError(np.linalg.LinAlgError):
+    """Mirror of TF's InvalidArgumentError 'Cholesky decomposition was not successful'."""
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m multi_fidelity_gpflow_b200.build` "
+            "(nvcc, sm_100a). This package has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, i, l, d = C.c_void_p, C.c_int, C.c_long, C.c_double
+    sig = {
+        "mfgp_version": ([], i),
+        "mfgp_create": ([i, C.POINTER(vp)], i),
+        "mfgp_destroy": ([vp], i),
+        "mfgp_set_stream": ([vp, vp], i),
+        "mfgp_set_async": ([vp, i], i),
+        "mfgp_sync": ([vp, C.POINTER(i)], i),
+        "mfgp_last_error": ([vp], C.c_char_p),
+        "mfgp_sm_count": ([vp], i),
+        "mfgp_cov": ([vp, vp, i, vp, i, i, vp, vp, l], i),
+        "mfgp_cov_diag": ([vp, vp, i, i, vp, vp], i),
+        "mfgp_gpr_nlml": ([vp, vp, vp, i, i, i, vp, d, vp], i),
+        "mfgp_gpr_nlml_grad": ([vp, vp, vp, i, i, i, vp, d, vp, vp], i),
+        "mfgp_gpr_predict": ([vp, vp, vp, i, i, i, vp, i, vp, d, vp, vp], i),
+        "mfgp_gpr_batched_nlml_grad": ([vp, vp, i, i, vp, l, i, vp, vp, vp, vp, vp], i),
+        "mfgp_svgp_elbo_grad": ([vp, vp, vp, vp, vp, vp, vp, vp, vp, d, vp, vp, vp, vp, vp, vp, vp, vp], i),
+        "mfgp_svgp_predict": ([vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp], i),
+        "mfgp_gemm": ([vp, C.c_char, C.c_char, i, i, i, d, vp, l, vp, l, d, vp, l], i),
+        "mfgp_potrf": ([vp, vp, i, l], i),
+        "mfgp_potrf_inv": ([vp, vp, i, l, vp, l], i),
+        "mfgp_fp64_peak": ([vp, i, i, C.POINTER(d)], i),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+    return lib
+
+
+_lib = _load()
+EXPORTED_SYMBOLS = [
+    "mfgp_version", "mfgp_create", "mfgp_destroy", "mfgp_set_stream", "mfgp_set_async", "mfgp_sync",
+    "mfgp_last_error", "mfgp_sm_count", "mfgp_cov", "mfgp_cov_diag", "mfgp_gpr_nlml", "mfgp_gpr_nlml_grad",
+    "mfgp_gpr_predict", "mfgp_gpr_batched_nlml_grad", "mfgp_svgp_elbo_grad", "mfgp_svgp_predict", "mfgp_gemm",
+    "mfgp_potrf", "mfgp_potrf_inv", "mfgp_fp64_peak",
+]
+
+
+class SvgpCfg(C.Structure):
+    _fields_ = [
+        ("L", C.c_int), ("M", C.c_int), ("P", C.c_int), ("B", C.c_int), ("d", C.c_int), ("hetero", C.c_int),
+        ("scale", C.c_double), ("kl_mult", C.c_double), ("jitter", C.c_double),
+    ]
+
+
+def _ptr(x):
+    """Raw address of a float64/int32 C-contiguous buffer (host ndarray or device tensor)."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        if not x.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return C.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):
+        if hasattr(x, "is_contiguous") and not x.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return C.c_void_p(x.data_ptr())
+    if hasattr(x, "__cuda_array_interface__"):
+        return C.c_void_p(x.__cuda_array_interface__["data"][0])
+    raise TypeError(f"unsupported buffer type {type(x)}")
+
+
+def as_f64(x):
+    """Host arrays -> contiguous float64 ndarray; device tensors pass through (must be float64)."""
+    if hasattr(x, "data_ptr") or hasattr(x, "__cuda_array_interface__"):
+        return x
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+class Handle:
+    """One per GPU per thread (include/mfgp.h threading contract)."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        rc = _lib.mfgp_create(device, C.byref(h))
+        if rc != 0:
+            raise MFGPError(f"mfgp_create(device={device}) failed with {rc}: no usable CUDA device (no CPU fallback)")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.mfgp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers -----------------------------------------------------------------------------
+    def _check(self, rc, what):
+        if rc == 0:
+            return
+        msg = _lib.mfgp_last_error(self._h).decode()
+        if rc > 0:
+            raise NotPositiveDefiniteError(f"{what}: {msg}")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise MFGPError(f"{what}: rc={rc}: {msg}")
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(_lib.mfgp_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None), "set_stream")
+
+    def set_async(self, flag: bool):
+        self._check(_lib.mfgp_set_async(self._h, int(flag)), "set_async")
+
+    def sync(self) -> int:
+        info = C.c_int(0)
+        self._check(_lib.mfgp_sync(self._h, C.byref(info)), "sync")
+        return info.value
+
+    @property
+    def sm_count(self):
+        return _lib.mfgp_sm_count(self._h)
+
+    # -- K1 ------------------------------------------------------------------------------------
+    def cov(self, X, X2, theta, out=None):
+        X = as_f64(X)
+        N, d = X.shape[0], X.shape[1] - 1
+        if X2 is not None:
+            X2 = as_f64(X2)
+            N2 = X2.shape[0]
+        else:
+            N2 = N
+        theta = as_f64(theta)
+        K = np.empty((N, N2)) if out is None else out
+        self._check(_lib.mfgp_cov(self._h, _ptr(X), N, _ptr(X2), N2, d, _ptr(theta), _ptr(K), K.shape[1] if K.ndim == 2 else N2), "mfgp_cov")
+        return K
+
+    def cov_diag(self, X, theta, out=None):
+        X = as_f64(X)
+        N, d = X.shape[0], X.shape[1] - 1
+        theta = as_f64(theta)
+        o = np.empty(N) if out is None else out
+        self._check(_lib.mfgp_cov_diag(self._h, _ptr(X), N, d, _ptr(theta), _ptr(o)), "mfgp_cov_diag")
+        return o
+
+    # -- exact GPR -----------------------------------------------------------------------------
+    def gpr_nlml(self, X, Y, theta, noise):
+        X, Y, theta = as_f64(X), as_f64(Y), as_f64(theta)
+        N, d, P = X.shape[0], X.shape[1] - 1, Y.shape[1]
+        out = np.empty(1)
+        self._check(_lib.mfgp_gpr_nlml(self._h, _ptr(X), _ptr(Y), N, d, P, _ptr(theta), float(noise), _ptr(out)), "mfgp_gpr_nlml")
+        return float(out[0])
+
+    def gpr_nlml_grad(self, X, Y, theta, noise):
+        X, Y, theta = as_f64(X), as_f64(Y), as_f64(theta)
+        N, d, P = X.shape[0], X.shape[1] - 1, Y.shape[1]
+        out, g = np.empty(1), np.empty(2 * d + 4)
+        self._check(
+            _lib.mfgp_gpr_nlml_grad(self._h, _ptr(X), _ptr(Y), N, d, P, _ptr(theta), float(noise), _ptr(out), _ptr(g)),
+            "mfgp_gpr_nlml_grad",
+        )
+        return float(out[0]), g
+
+    def gpr_predict(self, X, Y, Xs, theta, noise):
+        X, Y, Xs, theta = as_f64(X), as_f64(Y), as_f64(Xs), as_f64(theta)
+        N, d, P, Ns = X.shape[0], X.shape[1] - 1, Y.shape[1], Xs.shape[0]
+        mean, var = np.empty((Ns, P)), np.empty(Ns)
+        self._check(
+            _lib.mfgp_gpr_predict(self._h, _ptr(X), _ptr(Y), N, d, P, _ptr(Xs), Ns, _ptr(theta), float(noise), _ptr(mean), _ptr(var)),
+            "mfgp_gpr_predict",
+        )
+        return mean, var
+
+    def gpr_batched_nlml_grad(self, X, Y, thetas, noises, nlml=None, grad=None, info=None, want_grad=True, N=None, d=None, B=None, ldy=None):
+        """Host arrays or device tensors.  With device tensors pass N, d, B (and ldy) explicitly or via shapes."""
+        X, Y, thetas, noises = as_f64(X), as_f64(Y), as_f64(thetas), as_f64(noises)
+        N = X.shape[0] if N is None else N
+        d = X.shape[1] - 1 if d is None else d
+        B = Y.shape[1] if B is None else B
+        ldy = Y.shape[1] if ldy is None else ldy
+        if nlml is None:
+            nlml = np.empty(B)
+        if grad is None and want_grad:
+            grad = np.empty((B, 2 * d + 4))
+        rc = _lib.mfgp_gpr_batched_nlml_grad(
+            self._h, _ptr(X), N, d, _ptr(Y), ldy, B, _ptr(thetas), _ptr(noises), _ptr(nlml), _ptr(grad), _ptr(info)
+        )
+        self._check(rc, "mfgp_gpr_batched_nlml_grad")
+        return nlml, grad
+
+    # -- SVGP ----------------------------------------------------------------------------------
+    def svgp_elbo_grad(self, X, Y, Z, thetas, W, q_mu, q_sqrt, lik_var, scale=1.0, kl_mult=1.0, hetero=False,
+                       jitter=1e-6, want_grad=True):
+        X, Y, Z, thetas, q_mu, q_sqrt = map(as_f64, (X, Y, Z, thetas, q_mu, q_sqrt))
+        W = None if W is None else as_f64(W)
+        B, d = X.shape[0], X.shape[1] - 1
+        M, L = q_mu.shape
+        P = L if W is None else W.shape[0]
+        cfg = SvgpCfg(L, M, P, B, d, int(hetero), float(scale), float(kl_mult), float(jitter))
+        elbo, kl, glik = np.empty(1), np.empty(1), np.zeros(1)
+        if want_grad:
+            gZ, gth, gqm, gqs = np.zeros((M, d + 1)), np.zeros((L, 2 * d + 3)), np.zeros((M, L)), np.zeros((L, M, M))
+            gW = None if W is None else np.zeros((P, L))
+        else:
+            gZ = gth = gqm = gqs = gW = None
+        rc = _lib.mfgp_svgp_elbo_grad(
+            self._h, C.byref(cfg), _ptr(X), _ptr(Y), _ptr(Z), _ptr(thetas), _ptr(W), _ptr(q_mu), _ptr(q_sqrt),
+            float(lik_var), _ptr(elbo), _ptr(kl), _ptr(gZ), _ptr(gth), _ptr(gW), _ptr(gqm), _ptr(gqs),
+            _ptr(glik) if want_grad else None,
+        )
+        self._check(rc, "mfgp_svgp_elbo_grad")
+        return dict(elbo=float(elbo[0]), kl=float(kl[0]), g_Z=gZ, g_thetas=gth, g_W=gW, g_q_mu=gqm, g_q_sqrt=gqs,
+                    g_lik_var=float(glik[0]))
+
+    def svgp_predict(self, Xs, Z, thetas, W, q_mu, q_sqrt, jitter=1e-6):
+        Xs, Z, thetas, q_mu, q_sqrt = map(as_f64, (Xs, Z, thetas, q_mu, q_sqrt))
+        W = None if W is None else as_f64(W)
+        Ns, d = Xs.shape[0], Xs.shape[1] - 1
+        M, L = q_mu.shape
+        P = L if W is None else W.shape[0]
+        cfg = SvgpCfg(L, M, P, Ns, d, 0, 1.0, 1.0, float(jitter))
+        mean, var = np.empty((Ns, P)), np.empty((Ns, P))
+        rc = _lib.mfgp_svgp_predict(self._h, C.byref(cfg), _ptr(Xs), Ns, _ptr(Z), _ptr(thetas), _ptr(W), _ptr(q_mu),
+                                    _ptr(q_sqrt), _ptr(mean), _ptr(var))
+        self._check(rc, "mfgp_svgp_predict")
+        return mean, var
+
+    # -- building blocks -------------------------------------------------------------------------
+    def gemm(self, ta, tb, A, B, alpha=1.0, beta=0.0, C_in=None):
+        A, B = as_f64(A), as_f64(B)
+        m = A.shape[1] if ta else A.shape[0]
+        k = A.shape[0] if ta else A.shape[1]
+        n = B.shape[0] if tb else B.shape[1]
+        Cm = np.zeros((m, n)) if C_in is None else np.ascontiguousarray(C_in, dtype=np.float64).copy()
+        rc = _lib.mfgp_gemm(self._h, b"T" if ta else b"N", b"T" if tb else b"N", m, n, k, float(alpha), _ptr(A),
+                            A.shape[1], _ptr(B), B.shape[1], float(beta), _ptr(Cm), n)
+        self._check(rc, "mfgp_gemm")
+        return Cm
+
+    def potrf(self, A, want_inverse=False):
+        """A: [N, lda>=N even] lower-valid.  Returns L (in a copy) and optionally inv(L)."""
+        A = np.ascontiguousarray(A, dtype=np.float64).copy()
+        N, lda = A.shape
+        if want_inverse:
+            Wm = np.empty((N, lda))
+            self._check(_lib.mfgp_potrf_inv(self._h, _ptr(A), N, lda, _ptr(Wm), lda), "mfgp_potrf_inv")
+            return A, Wm
+        self._check(_lib.mfgp_potrf(self._h, _ptr(A), N, lda), "mfgp_potrf")
+        return A
+
+    def potrf_device(self, A_dev, N, lda):
+        self._check(_lib.mfgp_potrf(self._h, _ptr(A_dev), N, lda), "mfgp_potrf")
+
+    def fp64_peak(self, kind: int, iters: int = 20000) -> float:
+        out = C.c_double(0.0)
+        self._check(_lib.mfgp_fp64_peak(self._h, kind, iters, C.byref(out)), "mfgp_fp64_peak")
+        return out.value
+
+
+_default = {}
+
+
+def default_handle(device: int = 0) -> Handle:
+    if device not in _default:
+        _default[device] = Handle(device)
+    return _default[device]

@@ -1,0 +1,134 @@
+// common.cuh -- handle, stream-ordered temporaries, host/device pointer staging.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/mfgp.h"
+
+#define MFGP_ERR_ARG (-1)
+#define MFGP_ERR_CUDA (-2)
+#define MFGP_ERR_UNSUPPORTED (-3)
+
+struct mfgp_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;  // look-ahead stream for the panel chain
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int async = 0;
+    int sm_count = 148;
+    int* d_info = nullptr;   // device: first failing pivot (1-based), 0 = ok
+    int* h_info = nullptr;   // pinned mirror
+    char err[512] = {0};
+};
+
+inline int mfgp_fail(mfgp_handle* h, int code, const char* fmt, ...) {
+    if (h) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(h->err, sizeof(h->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                        \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return mfgp_fail((h), MFGP_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,    \
+                             cudaGetErrorString(_e));                                            \
+    } while (0)
+
+#define MFGP_TRY(expr)            \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc != 0) return _rc; \
+    } while (0)
+
+inline bool mfgp_is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Per-call scope: stream-ordered temporaries (cudaMallocAsync pool) + staged host I/O.
+struct Scope {
+    mfgp_handle* h;
+    std::vector<void*> temps;
+    struct Pending {
+        void* host;
+        const void* dev;
+        size_t bytes;
+    };
+    std::vector<Pending> outs;
+    bool ok = true;
+    bool host_out = false;
+    explicit Scope(mfgp_handle* hh) : h(hh) {}
+    ~Scope() {
+        for (void* p : temps) cudaFreeAsync(p, h->stream);
+    }
+    template <typename T>
+    T* alloc(size_t count, bool zero = false) {
+        void* p = nullptr;
+        size_t bytes = (count ? count : 1) * sizeof(T);
+        if (cudaMallocAsync(&p, bytes, h->stream) != cudaSuccess) {
+            snprintf(h->err, sizeof(h->err), "cudaMallocAsync(%zu bytes) failed: %s", bytes,
+                     cudaGetErrorString(cudaGetLastError()));
+            ok = false;
+            return nullptr;
+        }
+        temps.push_back(p);
+        if (zero) cudaMemsetAsync(p, 0, bytes, h->stream);
+        return static_cast<T*>(p);
+    }
+    // input: returns a device pointer holding `count` elements of `p` (copy if p is host)
+    template <typename T>
+    const T* in(const T* p, size_t count) {
+        if (!p) return nullptr;
+        if (mfgp_is_device_ptr(p)) return p;
+        T* d = alloc<T>(count);
+        if (!d) return nullptr;
+        if (cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) ok = false;
+        return d;
+    }
+    // output: returns a device pointer; if p is host the copy-back is queued for finish()
+    template <typename T>
+    T* out(T* p, size_t count, bool zero = false) {
+        if (!p) return nullptr;
+        if (mfgp_is_device_ptr(p)) {
+            if (zero) cudaMemsetAsync(p, 0, count * sizeof(T), h->stream);
+            return p;
+        }
+        T* d = alloc<T>(count, zero);
+        if (!d) return nullptr;
+        outs.push_back({p, d, count * sizeof(T)});
+        host_out = true;
+        return d;
+    }
+    // copy results back, synchronise unless (async && no host outputs), collect info
+    int finish() {
+        if (!ok) return mfgp_fail(h, MFGP_ERR_CUDA, "%s", h->err[0] ? h->err : "allocation / staging failed");
+        for (auto& o : outs) CUDA_TRY(h, cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaGetLastError());
+        if (h->async && !host_out) return 0;
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_info, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        int info = *h->h_info;
+        if (info != 0) {
+            CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), h->stream));
+            snprintf(h->err, sizeof(h->err), "Cholesky decomposition was not successful (pivot %d not positive)", info);
+        }
+        return info;
+    }
+};
+
+__host__ __device__ inline long round_up(long x, long m) { return (x + m - 1) / m * m; }

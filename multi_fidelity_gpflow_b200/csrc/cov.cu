@@ -1,0 +1,486 @@
+// cov.cu -- K1: fused multi-fidelity covariance assembly; K5: gradient contraction with
+// on-the-fly recomputation of dK/dtheta.
+//
+// Replaces LinearMultiFidelityKernel.K / K_diag (reference mfgpflow/linear.py:55-136): no
+// gather / meshgrid / scatter -- every output element selects its block from the two
+// fidelity flags:   K_ij = s_i s_j k_L(x_i, x_j) + h_i h_j k_delta(x_i, x_j)
+//   s = 1 (fid 0) | rho (fid 1) | 0 (anything else, linear.py:82), h = [fid == 1].
+// The squared distance uses the expanded form GPflow's SquaredExponential uses
+// (|a|^2 + |b|^2 - 2 a.b on length-scaled inputs), folded into the exp argument.
+//
+// Tiling: one CTA = 64 x 64 outputs, 256 threads, 4x4 register block per thread.  X tiles
+// are staged in shared memory already divided by the length-scales, k-major so that the
+// inner loop is 2+2 128-bit LDS per 16 DFMA.  A warp covers 4 thread-rows x 8 thread-cols,
+// so both the direct store (row segments) and the mirrored store of the symmetric case
+// (column segments) are written as full 128-byte lines with 128-bit STG.
+#include "cov.cuh"
+
+#include <cstdio>
+
+namespace {
+
+struct TileSmem {
+    double* aL;  // [d][64] scaled coords of the row points (kernel_L length-scales)
+    double* bL;  // [d][64] ... of the column points
+    double* aD;  // kernel_delta length-scales
+    double* bD;
+    double* haL;  // [64] -0.5 |a|^2
+    double* hbL;
+    double* haD;
+    double* hbD;
+    double* fa;  // [64] s_a * var_L
+    double* sb;  // [64] s_b
+    double* ga;  // [64] h_a * var_D
+    double* hb;  // [64] h_b
+    double* th;  // [2d+3] theta, then [2d] inverse length-scales (L then D)
+    int* flags;  // [2] any HF row / any HF col
+};
+
+__device__ inline TileSmem carve(double* base, int d) {
+    TileSmem t;
+    const int T = COV_TILE;
+    t.aL = base;
+    t.bL = t.aL + d * T;
+    t.aD = t.bL + d * T;
+    t.bD = t.aD + d * T;
+    t.haL = t.bD + d * T;
+    t.hbL = t.haL + T;
+    t.haD = t.hbL + T;
+    t.hbD = t.haD + T;
+    t.fa = t.hbD + T;
+    t.sb = t.fa + T;
+    t.ga = t.sb + T;
+    t.hb = t.ga + T;
+    t.th = t.hb + T;
+    t.flags = reinterpret_cast<int*>(t.th + 4 * MFGP_MAX_D + 4);
+    return t;
+}
+
+__host__ __device__ inline size_t tile_smem_bytes(int d) { return (size_t)(4 * d * COV_TILE + 8 * COV_TILE + 4 * MFGP_MAX_D + 4) * 8 + 16; }
+
+// Loads theta and both 64-point tiles.  Must be called by all 256 threads.
+__device__ inline void load_tiles(const TileSmem& t, const double* __restrict__ Xa, int Na, int i0,
+                                  const double* __restrict__ Xb, int Nb, int j0, int d,
+                                  const double* __restrict__ theta) {
+    const int tid = threadIdx.x;
+    const int T = COV_TILE;
+    if (tid < 2 * d + 3) t.th[tid] = theta[tid];
+    if (tid < 2) t.flags[tid] = 0;
+    __syncthreads();
+    if (tid < 2 * d) {
+        // inverse length-scales: th[2d+3 + k] = 1/lsL[k], th[3d+3 + k] = 1/lsD[k]
+        int k = tid < d ? tid : tid - d;
+        double ls = tid < d ? t.th[1 + k] : t.th[2 + d + k];
+        t.th[2 * d + 3 + tid] = 1.0 / ls;
+    }
+    __syncthreads();
+    if (tid < 2 * T) {
+        const int which = tid >> 6;  // 0: row points, 1: col points
+        const int r = tid & (T - 1);
+        const double* X = which ? Xb : Xa;
+        const int Np = which ? Nb : Na;
+        const int p = (which ? j0 : i0) + r;
+        const double rho = t.th[0], vL = t.th[1 + d], vD = t.th[2 + 2 * d];
+        double s = 0.0, h = 0.0;
+        bool live = false;
+        if (p < Np) {
+            double fid = X[(long)p * (d + 1) + d];
+            if (fid == 0.0) {
+                s = 1.0;
+                live = true;
+            } else if (fid == 1.0) {
+                s = rho;
+                h = 1.0;
+                live = true;
+            }
+        }
+        double nL = 0.0, nD = 0.0;
+        double* cL = which ? t.bL : t.aL;
+        double* cD = which ? t.bD : t.aD;
+        for (int k = 0; k < d; ++k) {
+            double x = live ? X[(long)p * (d + 1) + k] : 0.0;
+            double xl = x * t.th[2 * d + 3 + k];
+            double xd = x * t.th[3 * d + 3 + k];
+            cL[k * T + r] = xl;
+            cD[k * T + r] = xd;
+            nL = fma(xl, xl, nL);
+            nD = fma(xd, xd, nD);
+        }
+        if (which) {
+            t.hbL[r] = -0.5 * nL;
+            t.hbD[r] = -0.5 * nD;
+            t.sb[r] = s;
+            t.hb[r] = h;
+        } else {
+            t.haL[r] = -0.5 * nL;
+            t.haD[r] = -0.5 * nD;
+            t.fa[r] = s * vL;
+            t.ga[r] = h * vD;
+        }
+        if (h != 0.0) t.flags[which] = 1;  // benign race: all writers store 1
+    }
+    __syncthreads();
+}
+
+// acc[a][b] = sum_k A[k][r0+a] * B[k][col(b)],  col(b) = {2tx, 2tx+1, 32+2tx, 33+2tx}
+__device__ inline void tile_dots(const double* __restrict__ A, const double* __restrict__ B, int d, int r0, int tx,
+                                 double acc[4][4]) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < d; ++k) {
+        const double2 a01 = *reinterpret_cast<const double2*>(A + k * COV_TILE + r0);
+        const double2 a23 = *reinterpret_cast<const double2*>(A + k * COV_TILE + r0 + 2);
+        const double2 b01 = *reinterpret_cast<const double2*>(B + k * COV_TILE + 2 * tx);
+        const double2 b23 = *reinterpret_cast<const double2*>(B + k * COV_TILE + 32 + 2 * tx);
+        const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+        const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+    }
+}
+
+__device__ inline int col_of(int tx, int b) { return (b < 2 ? 0 : 32) + 2 * tx + (b & 1); }
+
+__device__ inline void tile_index(long t, int TJ, int symmetric, int& I, int& J) {
+    if (symmetric) {
+        long i = (long)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= t) ++i;
+        while (i * (i + 1) / 2 > t) --i;
+        I = (int)i;
+        J = (int)(t - i * (i + 1) / 2);
+    } else {
+        I = (int)(t / TJ);
+        J = (int)(t % TJ);
+    }
+}
+
+__global__ void __launch_bounds__(256) cov_kernel(CovArgs p, int TJ, int vec_ok) {
+    extern __shared__ __align__(16) double smem[];
+    const TileSmem t = carve(smem, p.d);
+    int I, J;
+    tile_index(blockIdx.x, TJ, p.symmetric, I, J);
+    const int b = blockIdx.z;
+    const int i0 = I * COV_TILE, j0 = J * COV_TILE;
+    load_tiles(t, p.Xa, p.Na, i0, p.Xb, p.Nb, j0, p.d, p.theta + (long)b * p.theta_stride);
+
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int tx = (w & 1) * 8 + (lane & 7);
+    const int ty = (w >> 1) * 4 + (lane >> 3);
+    const int r0 = ty * 4;
+
+    double acc[4][4], val[4][4];
+    tile_dots(t.aL, t.bL, p.d, r0, tx, acc);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int cc = col_of(tx, c);
+            val[a][c] = t.fa[r0 + a] * t.sb[cc] * exp(acc[a][c] + t.haL[r0 + a] + t.hbL[cc]);
+        }
+    if (t.flags[0] && t.flags[1]) {  // tile touches the HF x HF block: add the discrepancy GP
+        tile_dots(t.aD, t.bD, p.d, r0, tx, acc);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int cc = col_of(tx, c);
+                const double g = t.ga[r0 + a] * t.hb[cc];
+                if (g != 0.0) val[a][c] = fma(g, exp(acc[a][c] + t.haD[r0 + a] + t.hbD[cc]), val[a][c]);
+            }
+    }
+    if (p.symmetric && I == J) {
+        const double dg = p.diag_add_vec ? p.diag_add_vec[b] : p.diag_add;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (r0 + a == col_of(tx, c)) val[a][c] += dg;
+    }
+
+    double* __restrict__ K = p.K + (long)b * p.strideK;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int i = i0 + r0 + a;
+        if (i >= p.Na) continue;
+#pragma unroll
+        for (int hblk = 0; hblk < 2; ++hblk) {
+            const int j = j0 + hblk * 32 + 2 * tx;
+            double* dst = K + (long)i * p.ldk + j;
+            if (vec_ok && j + 1 < p.Nb) {
+                *reinterpret_cast<double2*>(dst) = make_double2(val[a][2 * hblk], val[a][2 * hblk + 1]);
+            } else {
+                if (j < p.Nb) dst[0] = val[a][2 * hblk];
+                if (j + 1 < p.Nb) dst[1] = val[a][2 * hblk + 1];
+            }
+        }
+    }
+    if (p.symmetric && p.mirror && I != J) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = j0 + col_of(tx, c);
+            if (j >= p.Nb) continue;
+            const int i = i0 + r0;
+            double* dst = K + (long)j * p.ldk + i;
+            if (vec_ok && i + 3 < p.Na) {
+                *reinterpret_cast<double2*>(dst) = make_double2(val[0][c], val[1][c]);
+                *reinterpret_cast<double2*>(dst + 2) = make_double2(val[2][c], val[3][c]);
+            } else {
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+                    if (i + a < p.Na) dst[a] = val[a][c];
+            }
+        }
+    }
+}
+
+__global__ void cov_diag_kernel(const double* __restrict__ X, int N, int d, const double* __restrict__ theta,
+                                long theta_stride, double* __restrict__ out, long out_stride) {
+    const int b = blockIdx.y;
+    const double* th = theta + (long)b * theta_stride;
+    const double rho = th[0], vL = th[1 + d], vD = th[2 + 2 * d];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const double fid = X[(long)i * (d + 1) + d];
+        double v = 0.0;
+        if (fid == 0.0) v = vL;
+        else if (fid == 1.0) v = fma(rho * rho, vL, vD);
+        out[(long)b * out_stride + i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: out[q] = sum_ij G_ij dK_ij/dtheta_q with dK recomputed in registers (never stored).
+// ---------------------------------------------------------------------------------------------
+__device__ inline double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <bool ROWGRAD>
+__global__ void __launch_bounds__(256) cov_grad_kernel(CovGradArgs p, int TJ, long ntiles) {
+    extern __shared__ __align__(16) double smem[];
+    const int d = p.d;
+    const TileSmem t = carve(smem, d);
+    double* red = smem + tile_smem_bytes(d) / 8;  // [8 warps][2d+4]
+    int I, J;
+    tile_index(blockIdx.x, TJ, p.sym_lower, I, J);
+    const int b = blockIdx.z;
+    const int i0 = I * COV_TILE, j0 = J * COV_TILE;
+    load_tiles(t, p.Xa, p.Na, i0, p.Xb, p.Nb, j0, d, p.theta + (long)b * p.theta_stride);
+
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int tx = (w & 1) * 8 + (lane & 7);
+    const int ty = (w >> 1) * 4 + (lane >> 3);
+    const int r0 = ty * 4;
+    const int nq = 2 * d + 4;
+    const bool hh = t.flags[0] && t.flags[1];
+
+    // weights G (with symmetric-lower multiplicity) for this thread's 4x4 block
+    const double* __restrict__ G = p.G + (long)b * p.strideG;
+    double TL[4][4], TD[4][4], acc[4][4];
+    double s_diag = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = i0 + r0 + a, j = j0 + col_of(tx, c);
+            double g = 0.0;
+            if (i < p.Na && j < p.Nb) {
+                if (p.sym_lower) {
+                    if (j < i) g = 2.0 * G[(long)i * p.ldg + j];
+                    else if (j == i) {
+                        g = G[(long)i * p.ldg + j];
+                        s_diag += g;
+                    }
+                } else {
+                    g = G[(long)i * p.ldg + j];
+                }
+            }
+            TL[a][c] = g;
+            TD[a][c] = g;
+        }
+    tile_dots(t.aL, t.bL, d, r0, tx, acc);
+    double s_vL = 0.0, s_rho = 0.0, s_vD = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int cc = col_of(tx, c);
+            const double kl = t.fa[r0 + a] * t.sb[cc] * exp(acc[a][c] + t.haL[r0 + a] + t.hbL[cc]);
+            const double v = TL[a][c] * kl;  // G_ij * K^L_ij
+            TL[a][c] = v;
+            s_vL += v;
+            // dK^L/drho = K^L (h_i + h_j) / rho ;  ga > 0 <=> h_a == 1
+            s_rho += v * ((t.ga[r0 + a] != 0.0 ? 1.0 : 0.0) + t.hb[cc]);
+        }
+    if (hh) {
+        tile_dots(t.aD, t.bD, d, r0, tx, acc);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int cc = col_of(tx, c);
+                const double g = t.ga[r0 + a] * t.hb[cc];
+                const double v = (g != 0.0) ? TD[a][c] * g * exp(acc[a][c] + t.haD[r0 + a] + t.hbD[cc]) : 0.0;
+                TD[a][c] = v;
+                s_vD += v;
+            }
+    }
+    double* myred = red + w * nq;
+    {
+        const double r_rho = warp_sum(s_rho), r_vL = warp_sum(s_vL), r_vD = warp_sum(s_vD), r_dg = warp_sum(s_diag);
+        if (lane == 0) {
+            myred[0] = r_rho;
+            myred[1 + d] = r_vL;
+            myred[2 + 2 * d] = hh ? r_vD : 0.0;
+            myred[3 + 2 * d] = r_dg;
+        }
+    }
+    double* __restrict__ rg = ROWGRAD ? p.rowgrad + (long)b * p.rowgrad_stride : nullptr;
+    for (int k = 0; k < d; ++k) {
+        double sL = 0.0, sD = 0.0;
+        double zr[4] = {0.0, 0.0, 0.0, 0.0};
+        const double ilL = t.th[2 * d + 3 + k], ilD = t.th[3 * d + 3 + k];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const double xa = t.aL[k * COV_TILE + r0 + a];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double df = t.bL[k * COV_TILE + col_of(tx, c)] - xa;
+                const double tv = TL[a][c] * df;
+                sL = fma(tv, df, sL);
+                if (ROWGRAD) zr[a] = fma(tv, ilL, zr[a]);
+            }
+        }
+        if (hh) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const double xa = t.aD[k * COV_TILE + r0 + a];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const double df = t.bD[k * COV_TILE + col_of(tx, c)] - xa;
+                    const double tv = TD[a][c] * df;
+                    sD = fma(tv, df, sD);
+                    if (ROWGRAD) zr[a] = fma(tv, ilD, zr[a]);
+                }
+            }
+        }
+        sL = warp_sum(sL);
+        sD = warp_sum(sD);
+        if (lane == 0) {
+            myred[1 + k] = sL;
+            myred[2 + d + k] = sD;
+        }
+        if (ROWGRAD) {
+            // dk/dx_i,k = K * (x_j - x_i)_k / ls_k^2 = K * df_scaled / ls_k ; reduce over the 8 lanes sharing a row
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                double z = zr[a];
+                z += __shfl_xor_sync(0xffffffffu, z, 1);
+                z += __shfl_xor_sync(0xffffffffu, z, 2);
+                z += __shfl_xor_sync(0xffffffffu, z, 4);
+                const int i = i0 + r0 + a;
+                if ((lane & 7) == 0 && i < p.Na && z != 0.0) atomicAdd(rg + (long)i * (d + 1) + k, p.rowgrad_scale * z);
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < nq) {
+        double s = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) s += red[ww * nq + tid];
+        p.partial[((long)b * ntiles + blockIdx.x) * nq + tid] = s;
+    }
+}
+
+__global__ void cov_grad_reduce_kernel(const double* __restrict__ partial, long ntiles, int d,
+                                       const double* __restrict__ theta, long theta_stride, double* __restrict__ out,
+                                       long out_stride, double scale, int accumulate) {
+    const int b = blockIdx.x;
+    const int nq = 2 * d + 4;
+    const double* th = theta + (long)b * theta_stride;
+    __shared__ double sh[8];
+    for (int q = 0; q < nq; ++q) {
+        double s = 0.0;
+        for (long t = threadIdx.x; t < ntiles; t += blockDim.x) s += partial[((long)b * ntiles + t) * nq + q];
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) tot += sh[ww];
+            double f = 1.0;
+            if (q == 0) f = 1.0 / th[0];                            // rho
+            else if (q <= d) f = 1.0 / th[q];                       // ls_L[k]: raw sum is in scaled coords -> / ls
+            else if (q == d + 1) f = 1.0 / th[d + 1];               // var_L
+            else if (q <= 2 * d + 1) f = 1.0 / th[q];               // ls_D[k]
+            else if (q == 2 * d + 2) f = 1.0 / th[2 * d + 2];       // var_D
+            double v = scale * f * tot;
+            double* o = out + (long)b * out_stride + q;
+            *o = accumulate ? (*o + v) : v;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+static bool aligned16(const void* p) { return (reinterpret_cast<size_t>(p) & 15) == 0; }
+
+int launch_cov(cudaStream_t s, const CovArgs& a) {
+    if (a.d < 1 || a.d > MFGP_MAX_D) return -1;
+    if (a.Na <= 0 || a.Nb <= 0 || a.batch <= 0) return 0;
+    const int TI = (a.Na + COV_TILE - 1) / COV_TILE, TJ = (a.Nb + COV_TILE - 1) / COV_TILE;
+    const long ntiles = a.symmetric ? (long)TI * (TI + 1) / 2 : (long)TI * TJ;
+    const size_t smem = tile_smem_bytes(a.d);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(MFGP_MAX_D));
+        attr_set = true;
+    }
+    const int vec_ok = aligned16(a.K) && (a.ldk % 2 == 0) && (a.strideK % 2 == 0);
+    dim3 grid((unsigned)ntiles, 1, a.batch);
+    cov_kernel<<<grid, 256, smem, s>>>(a, TJ, vec_ok);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int launch_cov_diag(cudaStream_t s, const double* X, int N, int d, const double* theta, long theta_stride,
+                    double* out, long out_stride, int batch) {
+    if (N <= 0 || batch <= 0) return 0;
+    dim3 grid((N + 255) / 256, batch);
+    cov_diag_kernel<<<grid, 256, 0, s>>>(X, N, d, theta, theta_stride, out, out_stride);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+static long grad_ntiles(const CovGradArgs& a) {
+    const int TI = (a.Na + COV_TILE - 1) / COV_TILE, TJ = (a.Nb + COV_TILE - 1) / COV_TILE;
+    return a.sym_lower ? (long)TI * (TI + 1) / 2 : (long)TI * TJ;
+}
+
+long cov_grad_partial_count(const CovGradArgs& a) { return (long)a.batch * grad_ntiles(a) * (2 * a.d + 4); }
+
+int launch_cov_grad(cudaStream_t s, const CovGradArgs& a) {
+    if (a.d < 1 || a.d > MFGP_MAX_D) return -1;
+    if (a.Na <= 0 || a.Nb <= 0 || a.batch <= 0) return 0;
+    const int TJ = (a.Nb + COV_TILE - 1) / COV_TILE;
+    const long ntiles = grad_ntiles(a);
+    const size_t smem = tile_smem_bytes(a.d) + (size_t)8 * (2 * a.d + 4) * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        const int mx = (int)(tile_smem_bytes(MFGP_MAX_D) + 8 * (2 * MFGP_MAX_D + 4) * 8);
+        cudaFuncSetAttribute(cov_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(cov_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        attr_set = true;
+    }
+    dim3 grid((unsigned)ntiles, 1, a.batch);
+    if (a.rowgrad) cov_grad_kernel<true><<<grid, 256, smem, s>>>(a, TJ, ntiles);
+    else cov_grad_kernel<false><<<grid, 256, smem, s>>>(a, TJ, ntiles);
+    cov_grad_reduce_kernel<<<a.batch, 256, 0, s>>>(a.partial, ntiles, a.d, a.theta, a.theta_stride, a.out,
+                                                   a.out_stride, a.out_scale, a.accumulate);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}

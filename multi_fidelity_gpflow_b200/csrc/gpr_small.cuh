@@ -1,0 +1,22 @@
+// gpr_small.cuh -- batched small-matrix GPR NLML+grad (one CTA per problem).
+#pragma once
+#include <cuda_runtime.h>
+
+#define MFGP_SMALL_MAX_N 64
+#define MFGP_SMALL_MAX_D 16
+
+struct SmallArgs {
+    const double* X;  // [N, d+1] shared by all problems
+    int N, d;
+    const double* Y;  // [N, ldy], problem b uses column b
+    long ldy;
+    int B;
+    const double* theta;  // [B, 2d+3]
+    const double* noise;  // [B]
+    double* nlml;         // [B]
+    double* grad;         // [B, 2d+4] or nullptr
+    int* info;            // [B] or nullptr
+    int* d_info;          // handle-wide first failure
+    int NP;               // filled by the launcher
+};
+int launch_gpr_small(cudaStream_t s, const SmallArgs& a);

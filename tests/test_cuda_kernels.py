@@ -1,0 +1,236 @@
+"""GPU parity tests of the CUDA building blocks (through the C-ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from oracle import mfgp_oracle as onp
+from oracle import mfgp_oracle_torch as otc
+from tests._helpers import goldens
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def h():
+    from multi_fidelity_gpflow_b200 import _lib
+
+    return _lib.Handle(0)
+
+
+def rand_theta(rng, d):
+    return onp.pack_theta(rng.uniform(0.5, 2.0), rng.uniform(0.3, 2.0, d), rng.uniform(0.5, 2.0),
+                          rng.uniform(0.3, 2.0, d), rng.uniform(0.2, 1.5))
+
+
+def rand_X(rng, n, d, frac_h=0.3, shuffle=True):
+    x = rng.random((n, d))
+    f = (rng.random(n) < frac_h).astype(float)
+    if not shuffle:
+        f = np.sort(f)
+    return np.hstack([x, f[:, None]])
+
+
+# ------------------------------------------------------------------------------------ K1 cov
+@pytest.mark.parametrize("N,N2,d", [(53, 10, 5), (1, 1, 1), (64, 64, 3), (65, 129, 10), (300, 1164, 10), (200, 77, 16)])
+def test_cov_rect(h, N, N2, d):
+    rng = np.random.default_rng(N * 1000 + N2)
+    X, X2, th = rand_X(rng, N, d), rand_X(rng, N2, d), rand_theta(rng, d)
+    K = h.cov(X, X2, th)
+    np.testing.assert_allclose(K, onp.mf_K(X, X2, th), rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("N,d", [(53, 5), (80, 1), (129, 10), (1164, 10), (2, 2)])
+def test_cov_symmetric_mirror(h, N, d):
+    rng = np.random.default_rng(N)
+    X, th = rand_X(rng, N, d), rand_theta(rng, d)
+    K = h.cov(X, None, th)
+    ref = onp.mf_K(X, None, th)
+    np.testing.assert_allclose(K, ref, rtol=1e-12, atol=1e-14)
+    assert np.array_equal(K, K.T)  # mirrored store: exactly symmetric
+
+
+def test_cov_dead_rows_and_nan_fidelity(h):
+    """Quirk Q1: fidelity not exactly 0/1 (0.5, 1-ulp, NaN) -> zero rows/cols (linear.py:82)."""
+    rng = np.random.default_rng(7)
+    X = rand_X(rng, 70, 4)
+    X[3, -1] = 0.5
+    X[10, -1] = np.nextafter(1.0, 0.0)
+    X[20, -1] = np.nan
+    X[20, 0] = np.nan
+    th = rand_theta(rng, 4)
+    K = h.cov(X, None, th)
+    ref = onp.mf_K(X, None, th)
+    assert np.all(K[[3, 10, 20]] == 0) and np.all(K[:, [3, 10, 20]] == 0)
+    np.testing.assert_allclose(K, ref, rtol=1e-12, atol=1e-14)
+    np.testing.assert_array_equal(h.cov_diag(X, th), onp.mf_K_diag(X, th))
+
+
+def test_cov_golden_datasets(h):
+    for name, d in (("hbs", 5), ("goku", 10)):
+        ds = onp.load_dataset(name)
+        th = onp.default_theta(d)
+        np.testing.assert_allclose(h.cov(ds["X"], None, th), onp.mf_K(ds["X"], None, th), rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(h.cov(ds["X"], ds["X_test"], th), onp.mf_K(ds["X"], ds["X_test"], th), rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(h.cov_diag(ds["X_test"], th), onp.mf_K_diag(ds["X_test"], th), rtol=1e-15)
+
+
+# ------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (53, 49, 53), (300, 1164, 300), (257, 130, 19), (2, 2, 2), (1000, 8, 1000), (64, 640, 16)])
+def test_gemm(h, ta, tb, m, n, k):
+    rng = np.random.default_rng(m + n + k)
+    ev = lambda x: x + (x & 1)
+    A = np.zeros((k, ev(m)) if ta else (m, ev(k)))
+    B = np.zeros((n, ev(k)) if tb else (k, ev(n)))
+    A[:, : (m if ta else k)] = rng.standard_normal((k, m) if ta else (m, k))
+    B[:, : (k if tb else n)] = rng.standard_normal((n, k) if tb else (k, n))
+    opA = (A.T if ta else A)[:m, :k]
+    opB = (B.T if tb else B)[:k, :n]
+    C0 = rng.standard_normal((m, n))
+    # the binding derives m/n/k from shapes: pass exact-shape views through padded buffers
+    from multi_fidelity_gpflow_b200 import _lib
+    import ctypes as C
+
+    out = C0.copy()
+    rc = _lib._lib.mfgp_gemm(h._h, b"T" if ta else b"N", b"T" if tb else b"N", m, n, k, 0.7, _lib._ptr(A), A.shape[1],
+                             _lib._ptr(B), B.shape[1], -0.3, _lib._ptr(out), n)
+    assert rc == 0, _lib._lib.mfgp_last_error(h._h)
+    ref = 0.7 * opA @ opB - 0.3 * C0
+    np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-11)
+
+
+# ------------------------------------------------------------------------------------ potrf / trtri
+@pytest.mark.parametrize("N", [1, 5, 53, 128, 129, 300, 640, 1164])
+def test_potrf_and_inverse(h, N):
+    rng = np.random.default_rng(N)
+    d = 4
+    X, th = rand_X(rng, N, d), rand_theta(rng, d)
+    K = onp.mf_K(X, None, th) + 1e-2 * np.eye(N)
+    lda = N + (N & 1)
+    A = np.zeros((N, lda))
+    A[:, :N] = np.tril(K)
+    L, W = h.potrf(A, want_inverse=True)
+    Lr = np.linalg.cholesky(K)
+    np.testing.assert_allclose(L[:, :N], Lr, rtol=1e-9, atol=1e-11)
+    assert np.all(np.triu(L[:, :N], 1) == 0)
+    Wr = np.linalg.inv(Lr)
+    np.testing.assert_allclose(W[:, :N], Wr, rtol=1e-8, atol=1e-8 * np.abs(Wr).max())
+    np.testing.assert_allclose(W[:, :N] @ Lr, np.eye(N), atol=1e-8)
+
+
+def test_potrf_not_positive_definite(h):
+    from multi_fidelity_gpflow_b200._lib import NotPositiveDefiniteError
+
+    A = np.eye(200)
+    A[150, 150] = -1.0
+    with pytest.raises(NotPositiveDefiniteError) as e:
+        h.potrf(A)
+    assert "151" in str(e.value)
+    h.potrf(np.eye(10))  # the handle recovers
+
+
+# ------------------------------------------------------------------------------------ exact GPR
+def test_gpr_golden_G1_G2(h):
+    G = goldens()
+    for name, d, key in (("hbs", 5, "G1_hbs_gpr_lml_init"), ("goku", 10, "G2_goku_gpr_lml_init")):
+        ds = onp.load_dataset(name)
+        nlml = h.gpr_nlml(ds["X"], ds["Y"], onp.default_theta(d), 1e-3)
+        assert abs(-nlml - G[key]["value"]) / abs(G[key]["value"]) < 1e-9  # north-star tolerance
+
+
+@pytest.mark.parametrize("name,d", [("hbs", 5), ("goku", 10), ("forrester", 1)])
+def test_gpr_nlml_grad_vs_oracle(h, name, d):
+    rng = np.random.default_rng(3)
+    ds = onp.forrester_dataset() if name == "forrester" else onp.load_dataset(name)
+    X, Y = ds["X"], ds["Y"]
+    for th in (onp.default_theta(d), rand_theta(rng, d)):
+        nlml, g = h.gpr_nlml_grad(X, Y, th, 1e-3)
+        lml, gth, gnz = otc.gpr_lml_value_and_grad(X, Y, th, 1e-3)
+        assert abs(nlml + lml) / abs(lml) < 1e-9
+        ref = -np.concatenate([gth, [gnz]])
+        np.testing.assert_allclose(g, ref, rtol=1e-7, atol=1e-7 * np.abs(ref).max())
+
+
+def test_gpr_predict_vs_oracle(h):
+    for name, d in (("hbs", 5), ("goku", 10)):
+        ds = onp.load_dataset(name)
+        th = onp.default_theta(d)
+        mean, var = h.gpr_predict(ds["X"], ds["Y"], ds["X_test"], th, 1e-3)
+        rm, rv = onp.gpr_predict(ds["X"], ds["Y"], ds["X_test"], th, 1e-3)
+        np.testing.assert_allclose(mean, rm, rtol=1e-8, atol=1e-8 * np.abs(rm).max())
+        np.testing.assert_allclose(var, rv, rtol=1e-8, atol=1e-8 * np.abs(rv).max())
+    ds = onp.forrester_dataset()
+    th = onp.default_theta(1)
+    for Xp in (ds["X_plot_L"], ds["X_plot_H"]):
+        mean, var = h.gpr_predict(ds["X"], ds["Y"], Xp, th, 1e-3)
+        rm, rv = onp.gpr_predict(ds["X"], ds["Y"], Xp, th, 1e-3)
+        np.testing.assert_allclose(mean, rm, rtol=1e-8, atol=1e-8 * np.abs(rm).max())
+        np.testing.assert_allclose(var, rv, rtol=1e-8, atol=1e-8 * np.abs(rv).max())
+
+
+# ------------------------------------------------------------------------------------ batched per-bin
+def test_batched_small_hbs_vs_oracle(h):
+    ds = onp.load_dataset("hbs")
+    X, Y = ds["X"], ds["Y"]
+    B, d = Y.shape[1], 5
+    rng = np.random.default_rng(0)
+    th = np.tile(onp.default_theta(d), (B, 1)) * np.exp(0.3 * rng.standard_normal((B, 2 * d + 3)))
+    nz = np.full(B, 1e-3) * np.exp(0.3 * rng.standard_normal(B))
+    nlml, grad = h.gpr_batched_nlml_grad(X, Y, th, nz)
+    vals, grads = otc.gpr_batched_value_and_grad(X, Y, th, nz)
+    np.testing.assert_allclose(nlml, -vals, rtol=1e-9)
+    for b in range(B):
+        np.testing.assert_allclose(grad[b], -grads[b], rtol=1e-7, atol=1e-7 * np.abs(grads[b]).max())
+
+
+def test_batched_identity_sum_equals_shared_and_G1(h):
+    ds = onp.load_dataset("hbs")
+    th = np.tile(onp.default_theta(5), (49, 1))
+    nlml, _ = h.gpr_batched_nlml_grad(ds["X"], ds["Y"], th, np.full(49, 1e-3))
+    g1 = goldens()["G1_hbs_gpr_lml_init"]["value"]
+    assert abs(-nlml.sum() - g1) / abs(g1) < 1e-9
+    shared = h.gpr_nlml(ds["X"], ds["Y"], onp.default_theta(5), 1e-3)
+    assert abs(nlml.sum() - shared) / abs(shared) < 1e-10
+
+
+@pytest.mark.parametrize("N,d,frac", [(1, 1, 0.0), (2, 3, 1.0), (17, 2, 0.5), (64, 16, 0.3), (33, 7, 0.0)])
+def test_batched_small_edge_shapes(h, N, d, frac):
+    rng = np.random.default_rng(N)
+    X = rand_X(rng, N, d, frac)
+    B = 5
+    Y = rng.standard_normal((N, B))
+    th = np.stack([rand_theta(rng, d) for _ in range(B)])
+    nz = rng.uniform(1e-3, 1e-1, B)
+    nlml, grad = h.gpr_batched_nlml_grad(X, Y, th, nz)
+    vals, grads = otc.gpr_batched_value_and_grad(X, Y, th, nz)
+    np.testing.assert_allclose(nlml, -vals, rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(grad, -grads, rtol=1e-7, atol=1e-7 * max(1.0, np.abs(grads).max()))
+
+
+def test_batched_blocked_path_forrester(h):
+    """N = 80 > 64 routes through the blocked (potrf/trtri/GEMM) batched path."""
+    ds = onp.forrester_dataset()
+    rng = np.random.default_rng(5)
+    B = 4
+    Y = np.hstack([ds["Y"] + 0.1 * rng.standard_normal(ds["Y"].shape) for _ in range(B)])
+    th = np.stack([rand_theta(rng, 1) for _ in range(B)])
+    nz = np.full(B, 1e-3)
+    nlml, grad = h.gpr_batched_nlml_grad(ds["X"], Y, th, nz)
+    vals, grads = otc.gpr_batched_value_and_grad(ds["X"], Y, th, nz)
+    np.testing.assert_allclose(nlml, -vals, rtol=1e-9)
+    np.testing.assert_allclose(grad, -grads, rtol=1e-7, atol=1e-7 * np.abs(grads).max())
+
+
+def test_batched_not_pd_reports_per_problem_info(h):
+    from multi_fidelity_gpflow_b200._lib import NotPositiveDefiniteError
+
+    rng = np.random.default_rng(1)
+    X = rand_X(rng, 20, 2, 0.0)
+    X[5] = X[4]  # duplicate point + negative noise -> not PD for problem 1 only
+    Y = rng.standard_normal((20, 3))
+    th = np.tile(onp.default_theta(2), (3, 1))
+    nz = np.array([1e-3, -1e-3, 1e-3])
+    info = np.zeros(3, dtype=np.int32)
+    with pytest.raises(NotPositiveDefiniteError):
+        h.gpr_batched_nlml_grad(X, Y, th, nz, info=info)
+    assert info[0] == 0 and info[2] == 0 and info[1] > 0
