@@ -35,8 +35,10 @@ typedef struct mfgp_handle mfgp_handle;
 int mfgp_version(void);
 int mfgp_create(int device, mfgp_handle** out);
 int mfgp_destroy(mfgp_handle* h);
-/* Run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL = handle's own. */
+/* Run on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL is the legacy default
+ * stream).  mfgp_reset_stream() returns to the handle's own non-blocking stream. */
 int mfgp_set_stream(mfgp_handle* h, void* cuda_stream);
+int mfgp_reset_stream(mfgp_handle* h);
 /* async != 0: calls whose outputs are all device pointers return without synchronising;
  * non-PD status is then collected by mfgp_sync(). */
 int mfgp_set_async(mfgp_handle* h, int async);

@@ -37,6 +37,7 @@ def _load():
         "mfgp_create": ([i, C.POINTER(vp)], i),
         "mfgp_destroy": ([vp], i),
         "mfgp_set_stream": ([vp, vp], i),
+        "mfgp_reset_stream": ([vp], i),
         "mfgp_set_async": ([vp, i], i),
         "mfgp_sync": ([vp, C.POINTER(i)], i),
         "mfgp_last_error": ([vp], C.c_char_p),
@@ -63,7 +64,7 @@ def _load():
 
 _lib = _load()
 EXPORTED_SYMBOLS = [
-    "mfgp_version", "mfgp_create", "mfgp_destroy", "mfgp_set_stream", "mfgp_set_async", "mfgp_sync",
+    "mfgp_version", "mfgp_create", "mfgp_destroy", "mfgp_set_stream", "mfgp_reset_stream", "mfgp_set_async", "mfgp_sync",
     "mfgp_last_error", "mfgp_sm_count", "mfgp_cov", "mfgp_cov_diag", "mfgp_gpr_nlml", "mfgp_gpr_nlml_grad",
     "mfgp_gpr_predict", "mfgp_gpr_batched_nlml_grad", "mfgp_svgp_elbo_grad", "mfgp_svgp_predict", "mfgp_gemm",
     "mfgp_potrf", "mfgp_potrf_inv", "mfgp_fp64_peak",
@@ -135,7 +136,11 @@ class Handle:
         raise MFGPError(f"{what}: rc={rc}: {msg}")
 
     def set_stream(self, cuda_stream_ptr):
-        self._check(_lib.mfgp_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None), "set_stream")
+        """cuda_stream_ptr: integer cudaStream_t (0 = legacy default stream); None = handle's own stream."""
+        if cuda_stream_ptr is None:
+            self._check(_lib.mfgp_reset_stream(self._h), "reset_stream")
+        else:
+            self._check(_lib.mfgp_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "set_stream")
 
     def set_async(self, flag: bool):
         self._check(_lib.mfgp_set_async(self._h, int(flag)), "set_async")

@@ -61,7 +61,12 @@ int mfgp_destroy(mfgp_handle* h) {
 
 int mfgp_set_stream(mfgp_handle* h, void* s) {
     CHECK_H(h);
-    h->stream = s ? static_cast<cudaStream_t>(s) : h->own_stream;
+    h->stream = static_cast<cudaStream_t>(s);
+    return 0;
+}
+int mfgp_reset_stream(mfgp_handle* h) {
+    CHECK_H(h);
+    h->stream = h->own_stream;
     return 0;
 }
 int mfgp_set_async(mfgp_handle* h, int async) {

@@ -28,7 +28,7 @@ struct TileSmem {
     double* hbL;
     double* haD;
     double* hbD;
-    double* fa;  // [64] s_a * var_L
+    double* fa;  // [64] s_a
     double* sb;  // [64] s_b
     double* ga;  // [64] h_a * var_D
     double* hb;  // [64] h_b
@@ -80,7 +80,7 @@ __device__ inline void load_tiles(const TileSmem& t, const double* __restrict__ 
         const double* X = which ? Xb : Xa;
         const int Np = which ? Nb : Na;
         const int p = (which ? j0 : i0) + r;
-        const double rho = t.th[0], vL = t.th[1 + d], vD = t.th[2 + 2 * d];
+        const double rho = t.th[0], vD = t.th[2 + 2 * d];
         double s = 0.0, h = 0.0;
         bool live = false;
         if (p < Np) {
@@ -114,7 +114,7 @@ __device__ inline void load_tiles(const TileSmem& t, const double* __restrict__ 
         } else {
             t.haL[r] = -0.5 * nL;
             t.haD[r] = -0.5 * nD;
-            t.fa[r] = s * vL;
+            t.fa[r] = s;
             t.ga[r] = h * vD;
         }
         if (h != 0.0) t.flags[which] = 1;  // benign race: all writers store 1
@@ -174,13 +174,15 @@ __global__ void __launch_bounds__(256) cov_kernel(CovArgs p, int TJ, int vec_ok)
     const int r0 = ty * 4;
 
     double acc[4][4], val[4][4];
+    const double vL = t.th[1 + p.d];
     tile_dots(t.aL, t.bL, p.d, r0, tx, acc);
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int cc = col_of(tx, c);
-            val[a][c] = t.fa[r0 + a] * t.sb[cc] * exp(acc[a][c] + t.haL[r0 + a] + t.hbL[cc]);
+            // (s_a s_b) and (h_a + h_b) are commutative: K(X,X) comes out exactly symmetric
+            val[a][c] = (t.fa[r0 + a] * t.sb[cc]) * vL * exp(acc[a][c] + (t.haL[r0 + a] + t.hbL[cc]));
         }
     if (t.flags[0] && t.flags[1]) {  // tile touches the HF x HF block: add the discrepancy GP
         tile_dots(t.aD, t.bD, p.d, r0, tx, acc);
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(256) cov_kernel(CovArgs p, int TJ, int vec_ok)
             for (int c = 0; c < 4; ++c) {
                 const int cc = col_of(tx, c);
                 const double g = t.ga[r0 + a] * t.hb[cc];
-                if (g != 0.0) val[a][c] = fma(g, exp(acc[a][c] + t.haD[r0 + a] + t.hbD[cc]), val[a][c]);
+                if (g != 0.0) val[a][c] += g * exp(acc[a][c] + (t.haD[r0 + a] + t.hbD[cc]));
             }
     }
     if (p.symmetric && I == J) {
@@ -247,7 +249,7 @@ __global__ void cov_diag_kernel(const double* __restrict__ X, int N, int d, cons
         const double fid = X[(long)i * (d + 1) + d];
         double v = 0.0;
         if (fid == 0.0) v = vL;
-        else if (fid == 1.0) v = fma(rho * rho, vL, vD);
+        else if (fid == 1.0) v = __dadd_rn(__dmul_rn(vL, __dmul_rn(rho, rho)), vD);  // K_diag_L * rho^2 + K_diag_delta (linear.py:127)
         out[(long)b * out_stride + i] = v;
     }
 }
@@ -305,13 +307,14 @@ __global__ void __launch_bounds__(256) cov_grad_kernel(CovGradArgs p, int TJ, lo
             TD[a][c] = g;
         }
     tile_dots(t.aL, t.bL, d, r0, tx, acc);
+    const double vL = t.th[1 + d];
     double s_vL = 0.0, s_rho = 0.0, s_vD = 0.0;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int cc = col_of(tx, c);
-            const double kl = t.fa[r0 + a] * t.sb[cc] * exp(acc[a][c] + t.haL[r0 + a] + t.hbL[cc]);
+            const double kl = (t.fa[r0 + a] * t.sb[cc]) * vL * exp(acc[a][c] + (t.haL[r0 + a] + t.hbL[cc]));
             const double v = TL[a][c] * kl;  // G_ij * K^L_ij
             TL[a][c] = v;
             s_vL += v;
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(256) cov_grad_kernel(CovGradArgs p, int TJ, lo
             for (int c = 0; c < 4; ++c) {
                 const int cc = col_of(tx, c);
                 const double g = t.ga[r0 + a] * t.hb[cc];
-                const double v = (g != 0.0) ? TD[a][c] * g * exp(acc[a][c] + t.haD[r0 + a] + t.hbD[cc]) : 0.0;
+                const double v = (g != 0.0) ? TD[a][c] * g * exp(acc[a][c] + (t.haD[r0 + a] + t.hbD[cc])) : 0.0;
                 TD[a][c] = v;
                 s_vD += v;
             }

@@ -124,7 +124,7 @@ def mf_K_diag(X, theta):
     rho, _, vL, _, vD = unpack_theta(theta, d)
     out = np.zeros(X.shape[0])
     out[X[:, -1] == 0] = vL
-    out[X[:, -1] == 1] = vL * rho * rho + vD
+    out[X[:, -1] == 1] = vL * (rho * rho) + vD  # :127  K_diag_L * rho**2 + K_diag_delta
     return out
 
 

@@ -31,7 +31,9 @@ def ev_time(fn, reps=3, warm=1):
 def main():
     out = {"gpu": torch.cuda.get_device_name(0)}
     h = _lib.Handle(0)
-    h.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    h.set_stream(stream.cuda_stream)
     out["dfma_tflops"] = h.fp64_peak(0, 40000) / 1e12
     out["dmma_tflops"] = h.fp64_peak(1, 40000) / 1e12
     print(out, flush=True)
