@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (contract in the task statement).
+
+Workload (BASELINE.json configs[1]): Ho-Bird-Shelton 2021 50LF-3HF multi-bin -- one linear
+multi-fidelity GPR per k-bin (49 bins, N = 53, d = 5), NLML + analytic gradient, batched:
+one STEP evaluates R independent hyper-parameter sets (restarts, seeded log-normal around the
+reference's initial values) for all 49 bins in one launch of the K6 kernel.
+metric = "NLML+grad evals/sec across bins", one eval = one full 49-bin NLML+gradient.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 (torchrun, one rank per GPU): bins/restarts shard across ranks with no data-path
+collective; every rank runs the same per-GPU batch (weak scaling); value = all ranks' evals /
+max-over-ranks device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NBINS, NPTS, DIM = 49, 53, 5
+METRIC = "NLML+grad evals/sec across bins"
+UNIT = "evals/s"
+ALG_FLOPS_PER_BIN = NPTS**3 + 4 * NPTS**2  # gpr_nlml_grad(N, P=1) = N^3 + 4 N^2 P
+
+
+def load_hbs():
+    from multi_fidelity_gpflow_b200.data import PowerSpecs
+
+    ps = PowerSpecs().read_from_npz(os.path.join(ROOT, "tests", "golden", "hbs.npz"))
+    return ps.training_arrays()
+
+
+def make_thetas(R, seed):
+    rng = np.random.default_rng(seed)
+    base = np.ones(2 * DIM + 3)
+    th = base * np.exp(0.3 * rng.standard_normal((R * NBINS, 2 * DIM + 3)))
+    return np.ascontiguousarray(th), np.full(R * NBINS, 1e-3)
+
+
+def config(R, extra=None):
+    c = {
+        "workload": "HBS2021 50LF-3HF multi-bin: 49 per-k-bin linear MF GPRs (N=53, d=5), NLML+grad, "
+                    f"R={R} hyper-parameter sets per step in one launch",
+        "bins": NBINS, "N": NPTS, "d": DIM, "restarts_per_step": R,
+        "l2_policy": "per-step inputs+outputs (theta, noise, nlml, grad) exceed the 126 MB L2",
+    }
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the CPU oracle (GPflow-equivalent restatement) on all host cores
+# ---------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    import torch
+
+    torch.set_num_threads(1)
+    from oracle import mfgp_oracle_torch as otc
+
+    X, Y, th, nz, lo, hi = args
+    acc = 0.0
+    for p in range(lo, hi):
+        b = p % NBINS
+        v, g, gn = otc.gpr_lml_value_and_grad(X, Y[:, b:b + 1], th[p], nz[p])
+        acc += v + g.sum() + gn
+    return acc
+
+
+def cpu_evals_per_sec(sample_evals, steps, warmup):
+    """Times `steps` passes over a bounded sample of `sample_evals` 49-bin evaluations."""
+    import multiprocessing as mp
+
+    X, Y = load_hbs()
+    th, nz = make_thetas(sample_evals, 0)
+    cores = os.cpu_count() or 1
+    nprob = sample_evals * NBINS
+    chunks = [(X, Y, th, nz, i * nprob // cores, (i + 1) * nprob // cores) for i in range(cores)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(X, Y, th, nz, 0, 1)] * cores)  # import / first-call warm-up in every worker
+        for _ in range(warmup):
+            pool.map(_cpu_worker, chunks)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_cpu_worker, chunks)
+        dt = time.perf_counter() - t0
+    return sample_evals * steps / dt, dt / steps, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = args.sample_evals
+    v, sec, cores = cpu_evals_per_sec(sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic restarts on the in-repo HBS2021 arrays",
+        "config": config(sample, {"note": "each step = bounded sample of the workload (sample_evals evals)"}),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} evals x 49 bins per step, torch-fp64 autograd oracle, one process per core; "
+                                   "GPflow/TensorFlow are not installable here, the oracle reproduces their recorded outputs G1-G7"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def run_mine(args):
+    import torch
+    import torch.distributed as dist
+
+    from multi_fidelity_gpflow_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # CPU baseline first (rank 0, N=1 only), in a separate process so no fork happens after CUDA init
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                              "--sample-evals", str(4 * args.sample_evals)], capture_output=True, text=True, cwd=ROOT)
+        for ln in out.stdout.splitlines():
+            if ln.startswith("{"):
+                cpu = json.loads(ln)["cpu_baseline"]
+
+    R = args.restarts
+    Xh, Yh = load_hbs()
+    thh, nzh = make_thetas(R, 1000 + rank)
+    nprob = R * NBINS
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    h = _lib.Handle(local)
+    h.set_stream(stream.cuda_stream)
+    X = torch.from_numpy(Xh).to(dev)
+    Y = torch.from_numpy(np.ascontiguousarray(Yh)).to(dev)
+    th = torch.from_numpy(thh).to(dev)
+    nz = torch.from_numpy(nzh).to(dev)
+    nlml = torch.empty(nprob, dtype=torch.float64, device=dev)
+    grad = torch.empty(nprob, 2 * DIM + 4, dtype=torch.float64, device=dev)
+    peak = max(h.fp64_peak(1, 20000), h.fp64_peak(0, 20000))  # measured FP64 pipe peak (DMMA / DFMA microbenchmarks)
+
+    h.set_async(True)
+
+    def step():
+        h.gpr_batched_nlml_grad(X, Y, th, nz, nlml=nlml, grad=grad)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    sec = e0.elapsed_time(e1) * 1e-3
+    clocks = sampler.stop()
+    assert h.sync() == 0
+    assert bool(torch.isfinite(nlml).all()) and bool(torch.isfinite(grad).all())
+    if world > 1:
+        t = torch.tensor([sec], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    value = world * R * args.steps / sec
+    kernel_sec = sec / args.steps  # one gpr_small_kernel launch per step
+    achieved = ALG_FLOPS_PER_BIN * nprob / kernel_sec
+
+    # e2e: same metric through the public binding with HOST (pinned) buffers, sync on return
+    h.set_async(False)
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    Xp, Yp, thp, nzp = pin(Xh), pin(np.ascontiguousarray(Yh)), pin(thh), pin(nzh)
+    nlml_h = torch.empty(nprob, dtype=torch.float64).pin_memory().numpy()
+    grad_h = torch.empty(nprob, 2 * DIM + 4, dtype=torch.float64).pin_memory().numpy()
+    for _ in range(max(1, args.warmup)):
+        h.gpr_batched_nlml_grad(Xp, Yp, thp, nzp, nlml=nlml_h, grad=grad_h)
+    barrier()
+    e2e_steps = max(3, args.steps // 2)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        h.gpr_batched_nlml_grad(Xp, Yp, thp, nzp, nlml=nlml_h, grad=grad_h)
+    e1.record(stream)
+    barrier()
+    e2e_sec = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        t = torch.tensor([e2e_sec], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_sec = float(t.item())
+    np.testing.assert_allclose(nlml_h, nlml.cpu().numpy(), rtol=1e-12)
+    h2d = Xp.nbytes + Yp.nbytes + thp.nbytes + nzp.nbytes
+    d2h = nlml_h.nbytes + grad_h.nbytes + 4
+
+    extra = {}
+    if world == 1 and not args.no_extra:  # second half of BASELINE's metric: fp64 Cholesky TFLOP/s at N = 16384
+        n = 16384
+        x = torch.randn(n, 64, dtype=torch.float64, device=dev)
+        a = x @ x.T + n * torch.eye(n, dtype=torch.float64, device=dev)
+        w = torch.empty_like(a)
+        h.set_async(True)
+        best = 1e30
+        for rep in range(3):
+            w.copy_(a)
+            e0.record(stream)
+            h.potrf_device(w, n, n)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            if rep:
+                best = min(best, e0.elapsed_time(e1) * 1e-3)
+        assert h.sync() == 0
+        extra = {"potrf_n16384_tflops": n**3 / 3 / best / 1e12, "potrf_n16384_frac_of_fp64_peak": n**3 / 3 / best / peak,
+                 "fp64_peak_tflops_measured": peak / 1e12}
+        del a, w, x
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic restarts on the in-repo HBS2021 arrays", "config": config(R, extra),
+            "roofline": {"bound": "tensor", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None, "kernel": "gpr_small_kernel",
+                         "peak_source": "measured live: FP64 pipe microbenchmark (DMMA m8n8k4 / DFMA), "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "alg_flops_per_bin": ALG_FLOPS_PER_BIN},
+            "cpu_baseline": cpu,
+            "e2e": {"value": world * R * e2e_steps / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": args.steps, "clocks": clocks,
+        }
+        tr = os.path.join(ROOT, "profiles", "traffic_gpr_small.json")
+        if os.path.exists(tr):
+            try:
+                line["roofline"]["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mine", choices=["mine", "reference"])
+    ap.add_argument("--restarts", type=int, default=16384, help="hyper-parameter sets per step (x49 bins)")
+    ap.add_argument("--sample-evals", type=int, default=256, help="CPU arm: 49-bin evals per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_mine(args)
+
+
+if __name__ == "__main__":
+    main()

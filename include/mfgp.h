@@ -70,11 +70,12 @@ int mfgp_gpr_predict(mfgp_handle* h, const double* X, const double* Y, int N, in
                      const double* Xs, int Ns, const double* theta, double noise,
                      double* mean, double* var);
 /* K6: "one GP per k-bin" (gpemulator_singlebin.py:1-14 design; BASELINE config 2): problem
- * b uses y = Y[:, b] (Y is [N, B] row-major with leading dimension ldy), theta[b, :],
- * noise[b].  nlml [B]; grad [B, 2d+4] or NULL; info [B] (int) or NULL.
+ * b uses y = Y[:, b % ycols] (Y is [N, ycols] row-major with leading dimension ldy),
+ * theta[b, :], noise[b]; B > ycols evaluates several hyper-parameter sets (restarts) per
+ * bin in one launch.  nlml [B]; grad [B, 2d+4] or NULL; info [B] (int) or NULL.
  * N <= 64 runs one CTA per problem entirely in shared memory. */
 int mfgp_gpr_batched_nlml_grad(mfgp_handle* h, const double* X, int N, int d, const double* Y,
-                               long ldy, int B, const double* theta, const double* noise,
+                               long ldy, int ycols, int B, const double* theta, const double* noise,
                                double* nlml, double* grad, int* info);
 
 /* ---- K7/K8: sparse variational GP (whitened, shared inducing points) -------------------

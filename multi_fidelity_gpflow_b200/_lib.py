@@ -47,7 +47,7 @@ def _load():
         "mfgp_gpr_nlml": ([vp, vp, vp, i, i, i, vp, d, vp], i),
         "mfgp_gpr_nlml_grad": ([vp, vp, vp, i, i, i, vp, d, vp, vp], i),
         "mfgp_gpr_predict": ([vp, vp, vp, i, i, i, vp, i, vp, d, vp, vp], i),
-        "mfgp_gpr_batched_nlml_grad": ([vp, vp, i, i, vp, l, i, vp, vp, vp, vp, vp], i),
+        "mfgp_gpr_batched_nlml_grad": ([vp, vp, i, i, vp, l, i, i, vp, vp, vp, vp, vp], i),
         "mfgp_svgp_elbo_grad": ([vp, vp, vp, vp, vp, vp, vp, vp, vp, d, vp, vp, vp, vp, vp, vp, vp, vp], i),
         "mfgp_svgp_predict": ([vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp], i),
         "mfgp_gemm": ([vp, C.c_char, C.c_char, i, i, i, d, vp, l, vp, l, d, vp, l], i),
@@ -204,19 +204,19 @@ class Handle:
         )
         return mean, var
 
-    def gpr_batched_nlml_grad(self, X, Y, thetas, noises, nlml=None, grad=None, info=None, want_grad=True, N=None, d=None, B=None, ldy=None):
-        """Host arrays or device tensors.  With device tensors pass N, d, B (and ldy) explicitly or via shapes."""
+    def gpr_batched_nlml_grad(self, X, Y, thetas, noises, nlml=None, grad=None, info=None, want_grad=True):
+        """Host arrays or device tensors.  Y is [N, ycols]; B = thetas.shape[0] problems, problem b uses
+        column b % ycols (B > ycols = several hyper-parameter sets per bin)."""
         X, Y, thetas, noises = as_f64(X), as_f64(Y), as_f64(thetas), as_f64(noises)
-        N = X.shape[0] if N is None else N
-        d = X.shape[1] - 1 if d is None else d
-        B = Y.shape[1] if B is None else B
-        ldy = Y.shape[1] if ldy is None else ldy
+        N, d = X.shape[0], X.shape[1] - 1
+        ycols = ldy = Y.shape[1]
+        B = thetas.shape[0]
         if nlml is None:
             nlml = np.empty(B)
         if grad is None and want_grad:
             grad = np.empty((B, 2 * d + 4))
         rc = _lib.mfgp_gpr_batched_nlml_grad(
-            self._h, _ptr(X), N, d, _ptr(Y), ldy, B, _ptr(thetas), _ptr(noises), _ptr(nlml), _ptr(grad), _ptr(info)
+            self._h, _ptr(X), N, d, _ptr(Y), ldy, ycols, B, _ptr(thetas), _ptr(noises), _ptr(nlml), _ptr(grad), _ptr(info)
         )
         self._check(rc, "mfgp_gpr_batched_nlml_grad")
         return nlml, grad

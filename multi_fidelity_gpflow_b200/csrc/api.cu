@@ -145,7 +145,7 @@ static int gpr_common(mfgp_handle* h, const double* X, const double* Y, int N, i
     double* dn = sc.out(nlml, 1);
     double* dg = grad ? sc.out(grad, 2 * d + 4) : nullptr;
     if (!sc.ok) return sc.finish();
-    int rc = gpr_nlml_grad_device(h, sc, dX, dY, P, 0, N, d, P, 1, dth, dnz, dn, dg, nullptr);
+    int rc = gpr_nlml_grad_device(h, sc, dX, dY, P, 0, 0, 0, N, d, P, 1, dth, dnz, dn, dg, nullptr);
     if (rc) return rc;
     return sc.finish();
 }
@@ -180,10 +180,10 @@ int mfgp_gpr_predict(mfgp_handle* h, const double* X, const double* Y, int N, in
     return sc.finish();
 }
 
-int mfgp_gpr_batched_nlml_grad(mfgp_handle* h, const double* X, int N, int d, const double* Y, long ldy, int B,
-                               const double* theta, const double* noise, double* nlml, double* grad, int* info) {
+int mfgp_gpr_batched_nlml_grad(mfgp_handle* h, const double* X, int N, int d, const double* Y, long ldy, int ycols,
+                               int B, const double* theta, const double* noise, double* nlml, double* grad, int* info) {
     CHECK_H(h);
-    if (!X || !Y || !theta || !noise || !nlml || N < 1 || B < 0 || d < 1 || d > MFGP_MAX_D || ldy < B)
+    if (!X || !Y || !theta || !noise || !nlml || N < 1 || B < 0 || d < 1 || d > MFGP_MAX_D || ycols < 1 || ldy < ycols)
         return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_gpr_batched_nlml_grad: bad argument");
     cudaSetDevice(h->device);
     if (B == 0) return 0;
@@ -198,7 +198,7 @@ int mfgp_gpr_batched_nlml_grad(mfgp_handle* h, const double* X, int N, int d, co
     if (!sc.ok) return sc.finish();
     if (N <= MFGP_SMALL_MAX_N && d <= MFGP_SMALL_MAX_D) {
         SmallArgs a{};
-        a.X = dX; a.N = N; a.d = d; a.Y = dY; a.ldy = ldy; a.B = B;
+        a.X = dX; a.N = N; a.d = d; a.Y = dY; a.ldy = ldy; a.ycols = ycols; a.B = B;
         a.theta = dth; a.noise = dnz; a.nlml = dn; a.grad = dg; a.info = di; a.d_info = h->d_info;
         if (launch_gpr_small(h->stream, a)) return mfgp_fail(h, MFGP_ERR_CUDA, "gpr_small launch failed");
     } else {
@@ -212,7 +212,7 @@ int mfgp_gpr_batched_nlml_grad(mfgp_handle* h, const double* X, int N, int d, co
         for (long b0 = 0; b0 < B; b0 += chunk) {
             const int nb = (int)((B - b0) < chunk ? (B - b0) : chunk);
             Scope inner(h);
-            int rc = gpr_nlml_grad_device(h, inner, dX, dY + b0, ldy, 1, N, d, 1, nb, dth + b0 * (2 * d + 3),
+            int rc = gpr_nlml_grad_device(h, inner, dX, dY, ldy, 1, (int)b0, ycols, N, d, 1, nb, dth + b0 * (2 * d + 3),
                                           dnz + b0, dn + b0, dg ? dg + b0 * (2 * d + 4) : nullptr, di ? di + b0 : nullptr);
             if (rc) return rc;
             if (!inner.ok) return inner.finish();

@@ -16,14 +16,15 @@ namespace {
 
 constexpr double LOG2PI = 1.8378770664093454835606594728112;
 
-// Yw[b][i][p] = Y[i*ldy + col0(b) + p]  (zero padded to Pp columns)
+// Yw[b][i][p] = Y[i*ldy + col0(b) + p]  (zero padded to Pp columns); col0(b) = ((b_off + b) * per_batch_cols) % ycols
 __global__ void pack_rhs_kernel(const double* __restrict__ Y, long ldy, int N, int P, int Pp, int per_batch_cols,
-                                double* __restrict__ Yw) {
+                                int b_off, int ycols, double* __restrict__ Yw) {
     const int b = blockIdx.y;
+    const long col0 = ycols > 0 ? ((long)(b_off + b) * per_batch_cols) % ycols : 0;
     const long tot = (long)N * Pp;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < tot; idx += (long)gridDim.x * blockDim.x) {
         const int i = (int)(idx / Pp), pcol = (int)(idx % Pp);
-        Yw[(long)b * tot + idx] = pcol < P ? Y[(long)i * ldy + (long)b * per_batch_cols + pcol] : 0.0;
+        Yw[(long)b * tot + idx] = pcol < P ? Y[(long)i * ldy + col0 + pcol] : 0.0;
     }
 }
 
@@ -72,8 +73,8 @@ struct Factor {
 };
 
 // Assemble + factor + invert + a = W Y for `batch` problems.  theta_d/noise_d are device arrays.
-int factor(mfgp_handle* h, Scope& sc, const double* X, const double* Y, long ldy, int per_batch_cols, int N, int d,
-           int P, int batch, const double* theta_d, const double* noise_d, int* info_vec, bool need_G, Factor& f) {
+int factor(mfgp_handle* h, Scope& sc, const double* X, const double* Y, long ldy, int per_batch_cols, int b_off,
+           int ycols, int N, int d, int P, int batch, const double* theta_d, const double* noise_d, int* info_vec, bool need_G, Factor& f) {
     cudaStream_t s = h->stream;
     f.ld = round_up(N, 2);
     f.strideM = (long)N * f.ld;
@@ -103,7 +104,7 @@ int factor(mfgp_handle* h, Scope& sc, const double* X, const double* Y, long ldy
     if (launch_potrf(s, ch)) return mfgp_fail(h, MFGP_ERR_CUDA, "potrf launch failed");
     if (launch_trtri(s, ch, f.W, f.ld, f.strideM, f.G)) return mfgp_fail(h, MFGP_ERR_CUDA, "trtri launch failed");
 
-    pack_rhs_kernel<<<dim3(64, batch), 256, 0, s>>>(Y, ldy, N, P, f.Pp, per_batch_cols, f.Yw);
+    pack_rhs_kernel<<<dim3(64, batch), 256, 0, s>>>(Y, ldy, N, P, f.Pp, per_batch_cols, b_off, ycols, f.Yw);
     GemmArgs g;  // a = W Yw
     g.transA = false; g.transB = false;
     g.M = N; g.N = f.Pp; g.K = N;
@@ -119,11 +120,11 @@ int factor(mfgp_handle* h, Scope& sc, const double* X, const double* Y, long ldy
 }  // namespace
 
 int gpr_nlml_grad_device(mfgp_handle* h, Scope& sc, const double* X, const double* Y, long ldy, int per_batch_cols,
-                         int N, int d, int P, int batch, const double* theta_d, const double* noise_d,
+                         int b_off, int ycols, int N, int d, int P, int batch, const double* theta_d, const double* noise_d,
                          double* nlml_d, double* grad_d, int* info_vec) {
     cudaStream_t s = h->stream;
     Factor f;
-    MFGP_TRY(factor(h, sc, X, Y, ldy, per_batch_cols, N, d, P, batch, theta_d, noise_d, info_vec, grad_d != nullptr, f));
+    MFGP_TRY(factor(h, sc, X, Y, ldy, per_batch_cols, b_off, ycols, N, d, P, batch, theta_d, noise_d, info_vec, grad_d != nullptr, f));
     nlml_kernel<<<batch, 256, 0, s>>>(f.a, N, f.Pp, P, f.logd, nlml_d);
     if (!grad_d) return 0;
 
@@ -183,7 +184,7 @@ int gpr_predict_device(mfgp_handle* h, Scope& sc, const double* X, const double*
                        double* var_d) {
     cudaStream_t s = h->stream;
     Factor f;
-    MFGP_TRY(factor(h, sc, X, Y, P, 0, N, d, P, 1, theta_d, noise_d, nullptr, false, f));
+    MFGP_TRY(factor(h, sc, X, Y, P, 0, 0, 0, N, d, P, 1, theta_d, noise_d, nullptr, false, f));
     const long lds = round_up(Ns, 2);
     double* Ks = sc.alloc<double>((size_t)N * lds);
     double* As = sc.alloc<double>((size_t)N * lds);

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(NTH) gpr_small_kernel(SmallArgs p) {
         }
         s.sv[tid] = sf;
         s.hv[tid] = hf;
-        s.yv[tid] = p.Y[(long)tid * p.ldy + prob];
+        s.yv[tid] = p.Y[(long)tid * p.ldy + prob % p.ycols];
     }
     __syncthreads();
     if (tid == 0) {  // ordered list of HF points (used by the discrepancy-kernel gradient pass)

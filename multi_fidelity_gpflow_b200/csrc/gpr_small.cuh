@@ -8,8 +8,9 @@
 struct SmallArgs {
     const double* X;  // [N, d+1] shared by all problems
     int N, d;
-    const double* Y;  // [N, ldy], problem b uses column b
+    const double* Y;  // [N, ldy], problem b uses column b % ycols
     long ldy;
+    int ycols;
     int B;
     const double* theta;  // [B, 2d+3]
     const double* noise;  // [B]
