@@ -1,0 +1,137 @@
+"""Shared machinery of the two SVGP models: gpflow.models.SVGP surface (elbo, prior_kl, predict_f,
+q_mu, q_sqrt, inducing_variable, kernel, likelihood, trainable_variables) over mfgp_svgp_*."""
+from __future__ import annotations
+
+import pickle
+
+import numpy as np
+
+from . import _lib
+from .base import Parameter, multiple_assign, parameter_dict
+
+
+class InducingPoints:
+    _param_order = ("Z",)
+
+    def __init__(self, Z):
+        self.Z = Parameter(np.asarray(Z, dtype=np.float64))
+
+
+class SharedIndependentInducingVariables:
+    _param_order = ("inducing_variable",)
+
+    def __init__(self, inducing_variable):
+        self.inducing_variable = inducing_variable
+
+
+def kmeans_inducing_points(X, num_inducing, random_state=42):
+    """KMeans on X INCLUDING the fidelity column, like the reference (singlebin_svgp.py:50-51; quirk Q1)."""
+    from sklearn.cluster import KMeans
+
+    return KMeans(n_clusters=num_inducing, random_state=random_state).fit(X).cluster_centers_
+
+
+class SVGPBase:
+    _param_order = ("kernel", "likelihood", "inducing_variable", "q_mu", "q_sqrt")
+    whiten = True
+
+    def _init_svgp(self, kernel, likelihood, Z, num_latent_gps, q_mu=None, q_sqrt=None, num_data=None, handle=None):
+        self._handle = handle
+        self.kernel = kernel
+        self.likelihood = likelihood
+        self.inducing_variable = SharedIndependentInducingVariables(InducingPoints(Z))
+        M = Z.shape[0]
+        self.num_latent_gps = num_latent_gps
+        self.num_data = num_data
+        self.q_mu = Parameter(np.zeros((M, num_latent_gps)) if q_mu is None else q_mu)
+        self.q_sqrt = Parameter(np.tile(np.eye(M), (num_latent_gps, 1, 1)) if q_sqrt is None else q_sqrt)
+        self.loss_history = []
+
+    @property
+    def handle(self):
+        return self._handle or _lib.default_handle()
+
+    @property
+    def Z(self):
+        return self.inducing_variable.inducing_variable.Z
+
+    # ---- parameter views -----------------------------------------------------------------------
+    def _thetas(self, d):
+        return np.stack([k.theta(d) for k in self.kernel.kernels])
+
+    def _W(self):
+        W = getattr(self.kernel, "W", None)
+        return None if W is None else W.numpy()
+
+    def _lik_var(self):
+        return float(np.ravel(self.likelihood.variance.numpy())[0])
+
+    @property
+    def trainable_variables(self):
+        """GPflow order seen in the reference notebooks: q_mu, q_sqrt, Z, [W], kernels..., likelihood.variance."""
+        vs = [self.q_mu, self.q_sqrt, self.Z]
+        W = getattr(self.kernel, "W", None)
+        if W is not None:
+            vs.append(W)
+        for k in self.kernel.kernels:
+            vs.extend([k.rho, k.kernel_L.lengthscales, k.kernel_L.variance, k.kernel_delta.lengthscales, k.kernel_delta.variance])
+        vs.append(self.likelihood.variance)
+        return [p for p in vs if p.trainable]
+
+    # ---- objective -----------------------------------------------------------------------------
+    def _call(self, data, want_grad, kl_multiplier=1.0):
+        X, Y = data
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        d = X.shape[1] - 1
+        scale = 1.0 if self.num_data is None else float(self.num_data) / X.shape[0]
+        return self.handle.svgp_elbo_grad(
+            X, Y, self.Z.numpy(), self._thetas(d), self._W(), self.q_mu.numpy(), np.tril(self.q_sqrt.numpy()),
+            self._lik_var(), scale=scale, kl_mult=kl_multiplier, hetero=self.likelihood.heteroscedastic, want_grad=want_grad,
+        ), d
+
+    def elbo(self, data):
+        return self._call(data, False)[0]["elbo"]
+
+    def prior_kl(self):
+        M, L = self.q_mu.shape
+        q_mu, Lq = self.q_mu.numpy(), np.tril(self.q_sqrt.numpy())
+        dg = np.diagonal(Lq, axis1=-2, axis2=-1)
+        return 0.5 * float(np.sum(q_mu * q_mu) - M * L - np.sum(np.log(dg * dg)) + np.sum(Lq * Lq))
+
+    def training_loss(self, data):
+        return -self.elbo(data)
+
+    def value_and_grad(self, data, variables=None, kl_multiplier=1.0):
+        """loss = -ELBO + (kl_multiplier - 1) KL; gradients w.r.t. the UNCONSTRAINED `variables`."""
+        variables = self.trainable_variables if variables is None else variables
+        r, d = self._call(data, True, kl_multiplier)
+        by = {id(self.q_mu): r["g_q_mu"], id(self.q_sqrt): r["g_q_sqrt"], id(self.Z): r["g_Z"]}
+        W = getattr(self.kernel, "W", None)
+        if W is not None:
+            by[id(W)] = r["g_W"]
+        for l, k in enumerate(self.kernel.kernels):
+            for p, gu in k.scatter_theta_grad(r["g_thetas"][l], d):
+                by[id(p)] = gu
+        lv = self.likelihood.variance
+        by[id(lv)] = lv.grad_to_unconstrained(np.full(lv.shape, r["g_lik_var"]) if lv.shape else r["g_lik_var"])
+        loss = -r["elbo"] + (kl_multiplier - 1.0) * r["kl"]
+        return loss, r["kl"], [np.asarray(by[id(p)], dtype=np.float64).reshape(p.shape) for p in variables]
+
+    def predict_f(self, Xnew, full_cov=False, full_output_cov=False):
+        if full_cov or full_output_cov:
+            raise NotImplementedError("the reference only calls predict_f(Xnew) (marginal variances)")
+        Xnew = np.ascontiguousarray(Xnew, dtype=np.float64)
+        d = Xnew.shape[1] - 1
+        return self.handle.svgp_predict(Xnew, self.Z.numpy(), self._thetas(d), self._W(), self.q_mu.numpy(),
+                                        np.tril(self.q_sqrt.numpy()))
+
+    # ---- checkpoint (pickle of gpflow.utilities.parameter_dict-style names) ------------------------
+    def save_model(self, filename):
+        with open(filename, "wb") as f:
+            pickle.dump(parameter_dict(self), f)
+
+    def _load_params(self, filename):
+        with open(filename, "rb") as f:
+            multiple_assign(self, pickle.load(f))
+        return self

@@ -1,0 +1,176 @@
+"""CPU tests of the host-side mirror: transforms, TF-Adam / CosineDecay emulation, SciPy packing,
+GPflow-style parameter names, W initialisers, fixture loader, multi-process sharding (gloo)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from multi_fidelity_gpflow_b200 import base, optimizers
+from multi_fidelity_gpflow_b200.data import PowerSpecs
+from multi_fidelity_gpflow_b200.dist import shard_range
+from oracle import mfgp_oracle as onp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_softplus_transform_roundtrip_and_chain_rule():
+    for lower in (0.0, 1e-6):
+        t = base.positive(lower)
+        theta = np.array([1e-3, 0.1, 1.0, 30.0]) + lower
+        u = t.inverse(theta)
+        np.testing.assert_allclose(t.forward(u), theta, rtol=1e-13)
+        eps = 1e-6
+        fd = (t.forward(u + eps) - t.forward(u - eps)) / (2 * eps)
+        np.testing.assert_allclose(t.dtheta_du(theta), fd, rtol=1e-6)
+    p = base.Parameter(1e-3, transform=base.positive(1e-6))
+    assert abs(p.numpy() - 1e-3) < 1e-18 + 1e-15
+
+
+def test_adam_matches_oracle_tf_adam():
+    rng = np.random.default_rng(0)
+    for decay in (None, 50):
+        p1 = base.Parameter(rng.standard_normal((3, 2)))
+        p2 = base.Parameter(rng.standard_normal(4))
+        ref = [p1.unconstrained.copy(), p2.unconstrained.copy()]
+        lr = optimizers.CosineDecay(0.1, decay) if decay else 0.1
+        opt = optimizers.Adam(lr)
+        oref = onp.TFAdam(lr=0.1, cosine_decay_steps=decay)
+        for step in range(60):
+            g = [rng.standard_normal((3, 2)), rng.standard_normal(4)]
+            g[1][2] = 0.0  # zero gradient => exactly zero update (quirk Q5 relies on it)
+            opt.apply_gradients(zip([x.copy() for x in g], [p1, p2]))
+            oref.step(ref, g)
+            assert np.array_equal(p1.unconstrained, ref[0]) and np.array_equal(p2.unconstrained, ref[1])
+
+
+def test_adam_float32_hypers():
+    opt = optimizers.Adam(0.1)
+    assert opt.lr == float(np.float32(0.1)) and opt.b1 == float(np.float32(0.9)) and opt.b2 == float(np.float32(0.999))
+    assert opt.lr != 0.1
+
+
+def test_scipy_packs_unconstrained_in_order():
+    a = base.Parameter(np.array([1.0, 2.0]), transform=base.positive())
+    b = base.Parameter(np.array([[0.5]]))
+    target = np.array([0.3, -0.2, 1.5])
+
+    def vg():
+        x = np.concatenate([a.unconstrained.ravel(), b.unconstrained.ravel()])
+        return 0.5 * np.sum((x - target) ** 2), [(x - target)[:2], (x - target)[2:].reshape(1, 1)]
+
+    res = optimizers.Scipy().minimize(vg, [a, b], options={"maxiter": 100})
+    assert res.success
+    np.testing.assert_allclose(np.concatenate([a.unconstrained, b.unconstrained.ravel()]), target, atol=1e-6)
+
+
+def test_parameter_dict_names_match_gpflow_layout():
+    from multi_fidelity_gpflow_b200.kernels import SeparateIndependent, SquaredExponential, replicate_mf_kernels
+    from multi_fidelity_gpflow_b200.likelihoods import Gaussian
+    from multi_fidelity_gpflow_b200.svgp_base import SVGPBase
+
+    m = SVGPBase()
+    ks = replicate_mf_kernels(SquaredExponential(lengthscales=np.ones(3)), SquaredExponential(lengthscales=np.ones(3)), 2)
+    m._init_svgp(SeparateIndependent(ks), Gaussian(), np.zeros((4, 4)), 2)
+    names = list(base.parameter_dict(m))
+    assert ".kernel.kernels[0].kernel_L.lengthscales" in names and ".kernel.kernels[1].rho" in names
+    assert ".likelihood.variance" in names and ".inducing_variable.inducing_variable.Z" in names
+    assert ".q_mu" in names and ".q_sqrt" in names
+    shapes = [p.shape for p in m.trainable_variables]
+    # order printed by the reference notebook: q_mu, q_sqrt, Z, then (rho, ls, var, ls, var) per kernel, likelihood
+    assert shapes[:3] == [(4, 2), (2, 4, 4), (4, 4)] and shapes[3:8] == [(1, 1), (3,), (), (3,), ()] and shapes[-1] == ()
+    # deep-copied base kernels: independent parameters per output (singlebin_svgp.py:39)
+    ks[0].kernel_L.variance.assign(2.0)
+    assert ks[1].kernel_L.variance.numpy() == 1.0
+
+
+def test_power_specs_loader_matches_oracle_loader():
+    for name in ("hbs", "goku"):
+        ps = PowerSpecs().read_from_npz(os.path.join(ROOT, "tests", "golden", f"{name}.npz"))
+        X, Y = ps.training_arrays()
+        ds = onp.load_dataset(name)
+        assert np.array_equal(X, ds["X"]) and np.array_equal(Y, ds["Y"])
+        Xt, Yt = ps.test_arrays()
+        assert np.array_equal(Xt, ds["X_test"]) and np.array_equal(Yt, ds["Y_test"])
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 49, 64, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from multi_fidelity_gpflow_b200.dist import dp_svgp_value_and_grad, gather_bins, shard_range
+    from oracle import mfgp_oracle as onp
+    from oracle import mfgp_oracle_torch as otc
+
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ds = onp.load_dataset("hbs")
+    X, Y = ds["X"], ds["Y"][:, :6]
+    rng = np.random.default_rng(0)
+    # (1) bins shard with no data-path collective; gather only assembles the answer
+    B = Y.shape[1]
+    th = np.tile(onp.default_theta(5), (B, 1)) * np.exp(0.1 * rng.standard_normal((B, 13)))
+    nz = np.full(B, 1e-3)
+    lo, hi = shard_range(B, rank, world)
+    vals, grads = otc.gpr_batched_value_and_grad(X, Y[:, lo:hi], th[lo:hi], nz[lo:hi])
+    full_v = gather_bins(vals, B)
+    full_g = gather_bins(grads, B)
+    # (2) data-parallel SVGP: rows shard, one all-reduce
+    M, L, P = 8, 3, 6
+    Z = X[rng.permutation(53)[:M]].copy()
+    ths = np.tile(onp.default_theta(5), (L, 1))
+    W = onp.initialize_W(P, L, 0.4, 0.2)
+    q_mu, q_sqrt = 0.1 * rng.standard_normal((M, L)), np.tile(0.3 * np.eye(M), (L, 1, 1))
+
+    def local_fn(Xr, Yr, scale, klm):
+        return otc.svgp_value_and_grad(Xr, Yr, Z, ths, q_mu, q_sqrt, 0.8, W, num_data=scale * Xr.shape[0], kl_mult=klm)
+
+    out = dp_svgp_value_and_grad(local_fn, X, Y, num_data=53, kl_mult=1.7)
+    if rank == 0:
+        q.put((full_v, full_g, out))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_matches_single_process():
+    import torch.multiprocessing as mp
+
+    from oracle import mfgp_oracle_torch as otc
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    full_v, full_g, out = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ds = onp.load_dataset("hbs")
+    X, Y = ds["X"], ds["Y"][:, :6]
+    rng = np.random.default_rng(0)
+    th = np.tile(onp.default_theta(5), (6, 1)) * np.exp(0.1 * rng.standard_normal((6, 13)))
+    v, g = otc.gpr_batched_value_and_grad(X, Y, th, np.full(6, 1e-3))
+    assert np.array_equal(full_v, v) and np.array_equal(full_g, g)  # no arithmetic crosses ranks: bit-identical
+    M, L, P = 8, 3, 6
+    Z = X[rng.permutation(53)[:M]].copy()
+    ths = np.tile(onp.default_theta(5), (L, 1))
+    W = onp.initialize_W(P, L, 0.4, 0.2)
+    q_mu, q_sqrt = 0.1 * rng.standard_normal((M, L)), np.tile(0.3 * np.eye(M), (L, 1, 1))
+    ref = otc.svgp_value_and_grad(X, Y, Z, ths, q_mu, q_sqrt, 0.8, W, num_data=53, kl_mult=1.7)
+    assert abs(out["elbo"] - ref["elbo"]) < 1e-11 * abs(ref["elbo"])
+    for k in ("g_Z", "g_thetas", "g_q_mu", "g_q_sqrt", "g_W"):
+        np.testing.assert_allclose(out[k], ref[k], rtol=1e-10, atol=1e-12 * np.abs(ref[k]).max())
+    assert abs(out["g_lik_var"] - ref["g_lik_var"]) < 1e-10 * abs(ref["g_lik_var"])
