@@ -20,4 +20,5 @@ struct SmallArgs {
     int* d_info;          // handle-wide first failure
     int NP;               // filled by the launcher
 };
-int launch_gpr_small(cudaStream_t s, const SmallArgs& a);
+int launch_gpr_small(cudaStream_t s, const SmallArgs& a);      // v1: one CTA per problem (DFMA)
+int launch_gpr_small_mma(cudaStream_t s, const SmallArgs& a);  // v2: one warp per problem (DMMA tiles)
