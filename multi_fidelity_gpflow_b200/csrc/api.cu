@@ -271,7 +271,7 @@ static int potrf_common(mfgp_handle* h, double* A, int N, long lda, double* Winv
     ch.A = dA; ch.N = N; ch.lda = lda; ch.strideA = 0; ch.batch = 1;
     ch.dinv = sc.alloc<double>((size_t)chol_dinv_count(N, 1));
     ch.logd = sc.alloc<double>(N);
-    ch.d_info = h->d_info;
+    ch.d_info = h->d_info; ch.aux = h->aux_stream; ch.ev = h->ev;
     if (!sc.ok) return sc.finish();
     if (launch_potrf(h->stream, ch)) return mfgp_fail(h, MFGP_ERR_CUDA, "potrf launch failed");
     if (Winv) {

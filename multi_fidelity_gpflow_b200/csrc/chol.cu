@@ -17,7 +17,6 @@
 namespace {
 
 constexpr int NB = CHOL_NB;
-constexpr int SP = NB + 1;  // odd pitch: conflict-free column and row walks
 
 struct DiagArgs {
     double* A;  // top-left of the diagonal block (batch 0)
@@ -32,128 +31,217 @@ struct DiagArgs {
     int* info_vec;
 };
 
-__global__ void __launch_bounds__(256, 1) potrf_diag_kernel(DiagArgs p) {
+// ---- DMMA tile helpers (same swizzled 8x8-tile layout as gpr_small_mma.cu) ---------------------------
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ int tslot(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
+__device__ __forceinline__ int tile_off(int r, int c) { return r * 8 + ((((c >> 1) ^ (r & 2))) << 1) + (c & 1); }
+
+constexpr int DT = NB / 8;                  // 16 tile rows
+constexpr int DTRI = DT * (DT + 1) / 2;     // 136 lower tiles
+constexpr int DIAG_THREADS = 128;           // 4 warps, one DMMA pipe each
+
+// One CTA factors a 128x128 diagonal block on the FP64 tensor path and inverts the factor:
+//   left-looking over 8-wide block columns; tile rows are dealt round-robin to the 4 warps;
+//   the 8x8 diagonal tile is factored redundantly in registers by one warp (no shuffles);
+//   W = L^-1 is then built column by column (columns are independent -> no block barriers).
+__global__ void __launch_bounds__(DIAG_THREADS, 1) potrf_diag_kernel(DiagArgs p) {
     extern __shared__ __align__(16) double sm[];
-    double* S = sm;                 // [128][129]: lower = L, strict upper = inv(L)^T
-    double* col = S + NB * SP;      // [2][128]
-    double* invd = col + 2 * NB;    // [128]
-    double* piv = invd + NB;        // [128]
+    double* Lt = sm;                 // [DTRI][64] L tiles (diagonal slots: L_kk, lower)
+    double* Wt = Lt + DTRI * 64;     // [DTRI][64] W = L^-1 tiles
+    double* lg = Wt + DTRI * 64;     // [DT] log-products of pivots per diagonal tile
     __shared__ int bad;
     const int nb = p.nb;
-    const int tid = threadIdx.x;
-    const int ti = tid >> 4, tk = tid & 15;
+    const int ntb = (nb + 7) / 8;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int cst = tile_off(g, 2 * t);
+    const int km0 = tile_off(g, t), km1 = tile_off(g, t + 4);
+    const int mm0 = tile_off(t, g), mm1 = tile_off(t + 4, g);
     const long bz = blockIdx.x;
     double* __restrict__ A = p.A + bz * p.strideA;
     if (tid == 0) bad = 0;
 
-    double r[8][8];
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const int i = ti + 16 * a, k = tk + 16 * b;
-            r[a][b] = (k <= i && i < nb) ? A[(long)i * p.lda + k] : 0.0;
-        }
+    // ---- load the lower triangle into tiles; pad with identity up to a multiple of 8 ---------------
+    for (int idx = tid; idx < ntb * (ntb + 1) / 2 * 64; idx += DIAG_THREADS) Lt[idx] = 0.0;
     __syncthreads();
-
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-        for (int jj = 0; jj < 16; ++jj) {
-            const int j = 16 * b + jj;
-            if (j >= nb) break;
-            double* buf = col + (j & 1) * NB;
-            if (tk == jj) {
-#pragma unroll
-                for (int a = 0; a < 8; ++a) {
-                    const int i = ti + 16 * a;
-                    if (i >= j && i < nb) buf[i] = r[a][b];
-                }
-            }
-            __syncthreads();
-            double pivot = buf[j];
-            if (!(pivot > 0.0)) {
-                if (tid == 0 && bad == 0) bad = p.k0 + j + 1;
-                pivot = nan("");
-            }
-            const double inv = 1.0 / pivot;
-#pragma unroll
-            for (int b2 = 0; b2 < 8; ++b2) {
-                if (b2 < b) continue;
-                const int k = tk + 16 * b2;
-                if (k <= j || k >= nb) continue;
-                const double ck = buf[k] * inv;
-#pragma unroll
-                for (int a = 0; a < 8; ++a) {
-                    const int i = ti + 16 * a;
-                    if (i >= k && i < nb) r[a][b2] = fma(-buf[i], ck, r[a][b2]);
-                }
-            }
-            if (tk == jj) {
-                const double ljj = sqrt(pivot), rinv = 1.0 / ljj;
-#pragma unroll
-                for (int a = 0; a < 8; ++a) {
-                    const int i = ti + 16 * a;
-                    if (i > j && i < nb) S[i * SP + j] = buf[i] * rinv;
-                    else if (i == j) {
-                        S[j * SP + j] = ljj;
-                        invd[j] = rinv;
-                        piv[j] = pivot;
-                    }
-                }
-            }
-        }
+    for (int idx = tid; idx < nb * NB; idx += DIAG_THREADS) {
+        const int r = idx >> 7, c = idx & (NB - 1);
+        if (c <= r) Lt[tslot(r >> 3, c >> 3) * 64 + tile_off(r & 7, c & 7)] = A[(long)r * p.lda + c];
     }
+    for (int r = nb + tid; r < ntb * 8; r += DIAG_THREADS) Lt[tslot(r >> 3, r >> 3) * 64 + tile_off(r & 7, r & 7)] = 1.0;
     __syncthreads();
 
-    // inverse: column jc by a lane pair; W[i][jc] kept at S[jc][i]
-    {
-        const int jc = tid >> 1, half = tid & 1;
-        const bool colok = jc < nb;
-        const double wjj = colok ? invd[jc] : 0.0;
-        for (int i = 1; i < nb; ++i) {
-            double acc = 0.0;
-            if (colok && i > jc) {
-                const double* Li = S + i * SP;
-                const double* Wj = S + jc * SP;
-                double acc2 = 0.0;
-                int k = jc + half;
-                if (k == jc) {  // first term uses the diagonal of W
-                    acc = Li[k] * wjj;
-                    k += 2;
+#pragma unroll 1
+    for (int kb = 0; kb < ntb; ++kb) {
+        // ---- update block column kb: tile (i, kb) -= sum_{k<kb} L_ik L_kbk^T, rows i = kb + warp + 4s --------
+        {
+            double acc[4][2];
+            int row[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                row[s] = kb + warp + 4 * s;
+                if (row[s] < ntb) {
+                    const double2 v = *reinterpret_cast<const double2*>(Lt + tslot(row[s], kb) * 64 + cst);
+                    acc[s][0] = v.x;
+                    acc[s][1] = v.y;
                 }
-                for (; k + 2 < i; k += 4) {
-                    acc = fma(Li[k], Wj[k], acc);
-                    acc2 = fma(Li[k + 2], Wj[k + 2], acc2);
-                }
-                for (; k < i; k += 2) acc = fma(Li[k], Wj[k], acc);
-                acc += acc2;
             }
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            if (colok && i > jc && half == 0) S[jc * SP + i] = -acc * invd[i];
+#pragma unroll 1
+            for (int k = 0; k < kb; ++k) {
+                const double* tb = Lt + tslot(kb, k) * 64;
+                const double b0 = tb[km0], b1 = tb[km1];
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                    if (row[s] < ntb) {
+                        const double* ta = Lt + tslot(row[s], k) * 64;
+                        dmma(acc[s][0], acc[s][1], -ta[km0], b0);
+                        dmma(acc[s][0], acc[s][1], -ta[km1], b1);
+                    }
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (row[s] < ntb) *reinterpret_cast<double2*>(Lt + tslot(row[s], kb) * 64 + cst) = make_double2(acc[s][0], acc[s][1]);
+        }
+        __syncthreads();
+        // ---- diagonal tile: redundant register Cholesky + inverse by the first warp ----------------------
+        if (warp == 0) {
+            double* td = Lt + tslot(kb, kb) * 64;
+            double* tw = Wt + tslot(kb, kb) * 64;
+            double a[8][8], rinv[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) a[r][c] = td[tile_off(r, c)];
+            double prod = 1.0;
+            int mybad = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                double piv = a[j][j];
+                if (!(piv > 0.0)) {
+                    if (!mybad) mybad = p.k0 + 8 * kb + j + 1;
+                    piv = nan("");
+                }
+                prod *= piv;
+                const double ri = rsqrt(piv);
+                rinv[j] = ri;
+                a[j][j] = piv * ri;  // L_jj = sqrt(piv)
+#pragma unroll
+                for (int i = j + 1; i < 8; ++i) a[i][j] *= ri;
+#pragma unroll
+                for (int k = j + 1; k < 8; ++k)
+#pragma unroll
+                    for (int i = k; i < 8; ++i) a[i][k] = fma(-a[i][j], a[k][j], a[i][k]);
+            }
+            const int c = lane & 7;
+            double w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                double s = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < i; ++k) s = fma(-a[i][k], w[k], s);
+                w[i] = s * rinv[i];
+            }
+            __syncwarp();
+            // all lanes hold the same L_kk: same-address stores collapse to one write each
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) td[tile_off(r, cc)] = (cc <= r) ? a[r][cc] : 0.0;
+            if (lane < 8) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) tw[tile_off(i, c)] = w[i];
+            }
+            if (lane == 0) {
+                lg[kb] = log(prod);
+                if (mybad && bad == 0) bad = mybad;
+            }
+        }
+        __syncthreads();
+        // ---- panel: L_ik = A_ik inv(L_kk)^T for rows i = kb + 1 + warp + 4s -------------------------------
+        {
+            const double* tw = Wt + tslot(kb, kb) * 64;
+            const double wb0 = tw[km0], wb1 = tw[km1];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int i = kb + 1 + warp + 4 * s;
+                if (i < ntb) {
+                    double* ta = Lt + tslot(i, kb) * 64;
+                    const double a0 = ta[km0], a1 = ta[km1];
+                    double c0 = 0.0, c1 = 0.0;
+                    dmma(c0, c1, a0, wb0);
+                    dmma(c0, c1, a1, wb1);
+                    __syncwarp();
+                    *reinterpret_cast<double2*>(ta + cst) = make_double2(c0, c1);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- write L back (lower, strict upper of the block zeroed) and log L_ii ------------------------------
+    for (int idx = tid; idx < nb * NB; idx += DIAG_THREADS) {
+        const int r = idx >> 7, c = idx & (NB - 1);
+        if (c < nb) A[(long)r * p.lda + c] = (c <= r) ? Lt[tslot(r >> 3, c >> 3) * 64 + tile_off(r & 7, c & 7)] : 0.0;
+    }
+    if (tid < nb) p.logd[bz * p.stride_logd + tid] = 0.0;  // per-row logs are folded into the first row of each tile
+    __syncthreads();
+    if (tid < ntb) p.logd[bz * p.stride_logd + 8 * tid] = 0.5 * lg[tid];
+
+    // ---- W = L^-1: column block j owned by warp j % 4 (columns are independent) ---------------------------
+#pragma unroll 1
+    for (int j = warp; j < ntb; j += 4) {
+#pragma unroll 1
+        for (int i = j + 1; i < ntb; ++i) {
+            double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;  // two interleaved accumulator chains
+            int k = j;
+#pragma unroll 1
+            for (; k + 1 < i; k += 2) {
+                const double* ta = Lt + tslot(i, k) * 64;
+                const double* tb = Wt + tslot(k, j) * 64;
+                const double* ta2 = Lt + tslot(i, k + 1) * 64;
+                const double* tb2 = Wt + tslot(k + 1, j) * 64;
+                dmma(c0, c1, ta[km0], tb[mm0]);
+                dmma(d0, d1, ta2[km0], tb2[mm0]);
+                dmma(c0, c1, ta[km1], tb[mm1]);
+                dmma(d0, d1, ta2[km1], tb2[mm1]);
+            }
+            if (k < i) {
+                const double* ta = Lt + tslot(i, k) * 64;
+                const double* tb = Wt + tslot(k, j) * 64;
+                dmma(c0, c1, ta[km0], tb[mm0]);
+                dmma(c0, c1, ta[km1], tb[mm1]);
+            }
+            c0 += d0;
+            c1 += d1;
+            double* tij = Wt + tslot(i, j) * 64;
+            *reinterpret_cast<double2*>(tij + cst) = make_double2(c0, c1);  // T = sum_k L_ik W_kj
+            __syncwarp();
+            const double* tw = Wt + tslot(i, i) * 64;
+            double w0 = 0.0, w1 = 0.0;
+            dmma(w0, w1, -tw[km0], tij[mm0]);
+            dmma(w0, w1, -tw[km1], tij[mm1]);
+            __syncwarp();
+            *reinterpret_cast<double2*>(tij + cst) = make_double2(w0, w1);
             __syncwarp();
         }
     }
     __syncthreads();
-
     double* __restrict__ D = p.dinv + bz * p.stride_dinv;
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int i = idx >> 7, j = idx & (NB - 1);
-        double w = 0.0;
-        if (i < nb && j < nb) {
-            A[(long)i * p.lda + j] = (j <= i) ? S[i * SP + j] : 0.0;
-            if (j < i) w = S[j * SP + i];
-            else if (j == i) w = invd[i];
-        }
-        D[idx] = w;
+    for (int idx = tid; idx < NB * NB; idx += DIAG_THREADS) {
+        const int r = idx >> 7, c = idx & (NB - 1);
+        D[idx] = (r < nb && c <= r) ? Wt[tslot(r >> 3, c >> 3) * 64 + tile_off(r & 7, c & 7)] : 0.0;
     }
-    if (tid < nb) p.logd[bz * p.stride_logd + tid] = 0.5 * log(piv[tid]);
     if (tid == 0 && bad) {
         atomicCAS(p.d_info, 0, bad);
         if (p.info_vec) atomicCAS(p.info_vec + bz, 0, bad);
     }
 }
 
-constexpr size_t DIAG_SMEM = (size_t)(NB * SP + 2 * NB + 2 * NB) * 8;
+constexpr size_t DIAG_SMEM = (size_t)(2 * DTRI * 64 + DT + 2) * 8;
 
 // W diagonal blocks <- dinv; everything else of W <- 0 (done by memset before)
 __global__ void place_diag_kernel(const double* __restrict__ dinv, long stride_dinv, int nblk, double* __restrict__ W,
@@ -179,9 +267,18 @@ int launch_potrf(cudaStream_t s, const CholArgs& a) {
     }
     const int nblk = chol_nblk(a.N);
     const long stride_dinv = (long)nblk * NB * NB;
+    // Look-ahead: the latency-bound chain  diag(k) -> panel(k)  runs on the aux stream and overlaps the
+    // FP64-bound trailing update of step k-1; the main stream only hands over the next block column early.
+    const bool la = a.aux != nullptr && a.ev != nullptr && nblk > 2;
+    cudaStream_t sp = la ? a.aux : s;  // stream of the panel chain
+    if (la) {
+        cudaEventRecord(a.ev[0], s);
+        cudaStreamWaitEvent(sp, a.ev[0], 0);
+    }
     for (int kb = 0; kb < nblk; ++kb) {
         const int k0 = kb * NB;
         const int nb = a.N - k0 < NB ? a.N - k0 : NB;
+        cudaEvent_t ev_col = la ? a.ev[2 * (kb & 1)] : nullptr, ev_panel = la ? a.ev[2 * (kb & 1) + 1] : nullptr;
         DiagArgs d;
         d.A = a.A + (long)k0 * a.lda + k0;
         d.lda = a.lda;
@@ -194,7 +291,8 @@ int launch_potrf(cudaStream_t s, const CholArgs& a) {
         d.stride_logd = a.N;
         d.d_info = a.d_info;
         d.info_vec = a.info_vec;
-        potrf_diag_kernel<<<a.batch, 256, DIAG_SMEM, s>>>(d);
+        if (la && kb > 0) cudaStreamWaitEvent(sp, ev_col, 0);  // block column kb fully updated
+        potrf_diag_kernel<<<a.batch, DIAG_THREADS, DIAG_SMEM, sp>>>(d);
         const int rem = a.N - k0 - nb;
         if (rem <= 0) break;
         double* panel = a.A + (long)(k0 + nb) * a.lda + k0;
@@ -209,18 +307,44 @@ int launch_potrf(cudaStream_t s, const CholArgs& a) {
         g.C = panel; g.ldc = a.lda; g.strideC = a.strideA;
         g.batch = a.batch;
         g.small_tiles = 0;
-        if (launch_gemm(s, g)) return -2;
-        // trailing <- trailing - panel panel^T  (lower tiles)
-        GemmArgs t;
-        t.transA = false; t.transB = true;
-        t.M = rem; t.N = rem; t.K = nb;
-        t.alpha = -1.0; t.beta = 1.0;
-        t.A = panel; t.lda = a.lda; t.strideA = a.strideA;
-        t.B = panel; t.ldb = a.lda; t.strideB = a.strideA;
-        t.C = a.A + (long)(k0 + nb) * a.lda + (k0 + nb); t.ldc = a.lda; t.strideC = a.strideA;
-        t.batch = a.batch;
-        t.lower_only = 1;
-        if (launch_gemm(s, t)) return -2;
+        if (launch_gemm(sp, g)) return -2;
+        if (la) {
+            cudaEventRecord(ev_panel, sp);
+            cudaStreamWaitEvent(s, ev_panel, 0);
+        }
+        // trailing <- trailing - panel panel^T  (lower tiles); with look-ahead the next block column first
+        const int ncol = la ? (rem < NB ? rem : NB) : 0;
+        if (la) {
+            GemmArgs c;
+            c.transA = false; c.transB = true;
+            c.M = rem; c.N = ncol; c.K = nb;
+            c.alpha = -1.0; c.beta = 1.0;
+            c.A = panel; c.lda = a.lda; c.strideA = a.strideA;
+            c.B = panel; c.ldb = a.lda; c.strideB = a.strideA;
+            c.C = a.A + (long)(k0 + nb) * a.lda + (k0 + nb); c.ldc = a.lda; c.strideC = a.strideA;
+            c.batch = a.batch;
+            c.small_tiles = 0;
+            if (launch_gemm(s, c)) return -2;
+            cudaEventRecord(a.ev[2 * ((kb + 1) & 1)], s);  // ev_col of step kb + 1
+        }
+        const int rest = rem - ncol;
+        if (rest > 0) {
+            double* p2 = panel + (long)ncol * a.lda;
+            GemmArgs t;
+            t.transA = false; t.transB = true;
+            t.M = rest; t.N = rest; t.K = nb;
+            t.alpha = -1.0; t.beta = 1.0;
+            t.A = p2; t.lda = a.lda; t.strideA = a.strideA;
+            t.B = p2; t.ldb = a.lda; t.strideB = a.strideA;
+            t.C = a.A + (long)(k0 + nb + ncol) * a.lda + (k0 + nb + ncol); t.ldc = a.lda; t.strideC = a.strideA;
+            t.batch = a.batch;
+            t.lower_only = 1;
+            if (launch_gemm(s, t)) return -2;
+        }
+    }
+    if (la) {  // the main stream owns the result again
+        cudaEventRecord(a.ev[0], sp);
+        cudaStreamWaitEvent(s, a.ev[0], 0);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

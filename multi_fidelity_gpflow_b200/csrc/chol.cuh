@@ -13,6 +13,8 @@ struct CholArgs {
     double* logd;   // [batch][N]: log(L_ii)
     int* d_info;    // first non-positive pivot (1-based global index), CAS'ed from 0
     int* info_vec;  // optional [batch]
+    cudaStream_t aux = nullptr;     // optional look-ahead stream for the diagonal-block / panel chain
+    cudaEvent_t* ev = nullptr;      // 4 events (disable-timing) when aux is set
 };
 inline int chol_nblk(int N) { return (N + CHOL_NB - 1) / CHOL_NB; }
 inline long chol_dinv_count(int N, int batch) { return (long)batch * chol_nblk(N) * CHOL_NB * CHOL_NB; }

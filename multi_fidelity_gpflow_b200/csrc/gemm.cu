@@ -99,7 +99,7 @@ struct KernelArgs {
 };
 
 template <int BM, int BN, int WM, int WN, bool TA, bool TB>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM == 128 ? 1 : 2)) dgemm_kernel(KernelArgs p) {
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN == 128 * 128 ? 1 : 2)) dgemm_kernel(KernelArgs p) {
     constexpr int NWN = BN / WN;
     constexpr int NT = (BM / WM) * NWN * 32;
     constexpr int MT = WM / 8, NTL = WN / 8;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM == 128 ? 1 : 2
         case KR_HI_MINIJ: khi = min(khi, min(i0 + BM, j0 + BN)); break;
         default: break;
     }
-    const int nk = khi > klo ? (khi - klo + BK - 1) / BK : 0;
+    const int nk = (khi > klo && p.alpha != 0.0) ? (khi - klo + BK - 1) / BK : 0;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
 
     auto load_stage = [&](int stage, int k0) {
@@ -142,11 +142,6 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM == 128 ? 1 : 2
     };
 
     double acc[MT][NTL][2];
-#pragma unroll
-    for (int m = 0; m < MT; ++m)
-#pragma unroll
-        for (int n = 0; n < NTL; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
-
     int arow[MT], bcol[NTL];
 #pragma unroll
     for (int m = 0; m < MT; ++m) arow[m] = frag_row<A_KM>(wm0, m, g);
@@ -158,6 +153,12 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM == 128 ? 1 : 2
         if (s < nk) load_stage(s, klo + s * BK);
         cp_async_commit();
     }
+
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int n = 0; n < NTL; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+
     for (int it = 0; it < nk; ++it) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -181,38 +182,71 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM == 128 ? 1 : 2
     }
     cp_async_wait<0>();
 
-    // ---- epilogue: C = alpha * acc + beta * C ---------------------------------------------
+    // ---- epilogue through shared memory -----------------------------------------------------------
+    // The accumulator fragments own 16-byte pieces scattered over 8 rows; reading/writing C straight from
+    // them half-uses every 128-byte line and starves on outstanding-miss slots (measured: the beta*C read
+    // ran at 1.6 TB/s).  Instead the C tile is moved with full-line cp.async / 128-bit stores and the
+    // fragments touch only shared memory.  The pipeline buffers are free at this point.
+    constexpr int CP = (BM * (BN + 2) * 8 <= STAGES * STAGE_BYTES) ? BN + 2 : BN;  // padded pitch (doubles)
+    double* ct = reinterpret_cast<double*>(smem_raw);
     const double alpha = p.alpha, beta = p.beta;
-    auto store2 = [&](int i, int j, double v0, double v1) {  // columns j, j+1 of row i
-        if (i >= p.M || j >= p.N) return;
-        double* dst = C + (long)i * p.ldc + j;
-        if (p.vec_ok && j + 1 < p.N) {
-            double2 o = make_double2(alpha * v0, alpha * v1);
-            if (beta != 0.0) {
-                const double2 old = *reinterpret_cast<const double2*>(dst);
-                o.x = fma(beta, old.x, o.x);
-                o.y = fma(beta, old.y, o.y);
+    const bool full = p.vec_ok && (i0 + BM <= p.M) && (j0 + BN <= p.N);
+    __syncthreads();  // every warp is done reading the last stage
+    if (beta != 0.0) {
+        if (full) {
+#pragma unroll 4
+            for (int idx = tid; idx < BM * BN / 2; idx += NT) {
+                const int r = idx / (BN / 2), c = idx % (BN / 2);
+                cp_async16(sbase + (r * CP + 2 * c) * 8, C + (long)(i0 + r) * p.ldc + j0 + 2 * c, 16);
             }
-            *reinterpret_cast<double2*>(dst) = o;
+            cp_async_commit();
+            cp_async_wait<0>();
         } else {
-            dst[0] = beta != 0.0 ? fma(beta, dst[0], alpha * v0) : alpha * v0;
-            if (j + 1 < p.N) dst[1] = beta != 0.0 ? fma(beta, dst[1], alpha * v1) : alpha * v1;
+            for (int idx = tid; idx < BM * BN; idx += NT) {
+                const int r = idx / BN, c = idx % BN;
+                ct[r * CP + c] = (i0 + r < p.M && j0 + c < p.N) ? C[(long)(i0 + r) * p.ldc + j0 + c] : 0.0;
+            }
         }
+        __syncthreads();
+    }
+    auto merge2 = [&](int r, int c, double v0, double v1) {  // tile-local row r, columns c, c+1 (c even)
+        double2* q = reinterpret_cast<double2*>(ct + r * CP + c);
+        double2 o = make_double2(alpha * v0, alpha * v1);
+        if (beta != 0.0) {
+            const double2 old = *q;
+            o.x = fma(beta, old.x, o.x);
+            o.y = fma(beta, old.y, o.y);
+        }
+        *q = o;
     };
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
-        const int i = i0 + arow[m];
+        const int r = arow[m];
         if (B_KM) {
             // fragment pair (2q, 2q+1) holds columns 16q + 4t + {0,1,2,3}
 #pragma unroll
             for (int q = 0; q < NTL / 2; ++q) {
-                const int j = j0 + wn0 + q * 16 + 4 * t;
-                store2(i, j, acc[m][2 * q][0], acc[m][2 * q + 1][0]);
-                store2(i, j + 2, acc[m][2 * q][1], acc[m][2 * q + 1][1]);
+                const int c = wn0 + q * 16 + 4 * t;
+                merge2(r, c, acc[m][2 * q][0], acc[m][2 * q + 1][0]);
+                merge2(r, c + 2, acc[m][2 * q][1], acc[m][2 * q + 1][1]);
             }
         } else {
 #pragma unroll
-            for (int n = 0; n < NTL; ++n) store2(i, j0 + wn0 + n * 8 + 2 * t, acc[m][n][0], acc[m][n][1]);
+            for (int n = 0; n < NTL; ++n) merge2(r, wn0 + n * 8 + 2 * t, acc[m][n][0], acc[m][n][1]);
+        }
+    }
+    __syncthreads();
+    if (full) {
+#pragma unroll 4
+        for (int idx = tid; idx < BM * BN / 2; idx += NT) {
+            const int r = idx / (BN / 2), c = idx % (BN / 2);
+            *reinterpret_cast<double2*>(C + (long)(i0 + r) * p.ldc + j0 + 2 * c) =
+                *reinterpret_cast<const double2*>(ct + r * CP + 2 * c);
+        }
+    } else {
+        for (int idx = tid; idx < BM * BN; idx += NT) {
+            const int r = idx / BN, c = idx % BN;
+            if (i0 + r < p.M && j0 + c < p.N) C[(long)(i0 + r) * p.ldc + j0 + c] = ct[r * CP + c];
         }
     }
 }
@@ -232,8 +266,9 @@ int launch_cfg(cudaStream_t s, const GemmArgs& a, const KernelArgs& ka) {
 }
 
 template <bool TA, bool TB>
-int launch_t(cudaStream_t s, const GemmArgs& a, const KernelArgs& ka, bool small_tiles) {
-    if (small_tiles) return launch_cfg<64, 64, 32, 32, TA, TB>(s, a, ka);
+int launch_t(cudaStream_t s, const GemmArgs& a, const KernelArgs& ka, int cfg) {
+    if (cfg == 1) return launch_cfg<64, 64, 32, 32, TA, TB>(s, a, ka);
+    if (cfg == 2) return launch_cfg<128, 64, 64, 32, TA, TB>(s, a, ka);
     return launch_cfg<128, 128, 64, 32, TA, TB>(s, a, ka);
 }
 
@@ -252,14 +287,16 @@ int launch_gemm(cudaStream_t s, const GemmArgs& a) {
     ka.krange = a.krange; ka.lower_only = a.lower_only;
     ka.batch = a.batch; ka.strideA2 = a.strideA2; ka.strideB2 = a.strideB2; ka.strideC2 = a.strideC2;
     ka.vec_ok = al16(a.C) && !(a.ldc & 1) && !(a.strideC & 1) && !(a.strideC2 & 1);
-    bool small_tiles;
-    if (a.small_tiles >= 0) small_tiles = a.small_tiles != 0;
+    // tile config: 0 = 128x128 (1 CTA/SM; the only one safe for the in-place panel solve), 1 = 64x64,
+    // 2 = 128x64 (2 CTAs/SM: one CTA's prologue/epilogue hides behind the other's main loop) -- the default.
+    int cfg;
+    if (a.small_tiles >= 0) cfg = a.small_tiles;
     else {
-        const long ctas128 = (long)((a.M + 127) / 128) * ((a.N + 127) / 128) * a.batch * a.batch2;
-        small_tiles = ctas128 < 148;
+        const long ctas = (long)((a.M + 127) / 128) * ((a.N + 63) / 64) * a.batch * a.batch2;
+        cfg = ctas < 2 * 148 ? 1 : 2;
     }
-    if (!a.transA && !a.transB) return launch_t<false, false>(s, a, ka, small_tiles);
-    if (!a.transA && a.transB) return launch_t<false, true>(s, a, ka, small_tiles);
-    if (a.transA && !a.transB) return launch_t<true, false>(s, a, ka, small_tiles);
-    return launch_t<true, true>(s, a, ka, small_tiles);
+    if (!a.transA && !a.transB) return launch_t<false, false>(s, a, ka, cfg);
+    if (!a.transA && a.transB) return launch_t<false, true>(s, a, ka, cfg);
+    if (a.transA && !a.transB) return launch_t<true, false>(s, a, ka, cfg);
+    return launch_t<true, true>(s, a, ka, cfg);
 }

@@ -34,7 +34,7 @@ struct GemmArgs {
     long strideA2 = 0, strideB2 = 0, strideC2 = 0;
     int krange = KR_FULL;  // OR of one KR_LO_* and one KR_HI_*
     int lower_only = 0;    // skip tiles strictly above the diagonal (symmetric / triangular outputs)
-    int small_tiles = -1;  // -1 auto, 0 force 128x128, 1 force 64x64
+    int small_tiles = -1;  // tile config: -1 auto, 0 = 128x128, 1 = 64x64, 2 = 128x64
 };
 
 int launch_gemm(cudaStream_t s, const GemmArgs& a);

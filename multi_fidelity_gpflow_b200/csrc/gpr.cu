@@ -100,7 +100,7 @@ int factor(mfgp_handle* h, Scope& sc, const double* X, const double* Y, long ldy
 
     CholArgs ch{};
     ch.A = f.K; ch.N = N; ch.lda = f.ld; ch.strideA = f.strideM; ch.batch = batch;
-    ch.dinv = f.dinv; ch.logd = f.logd; ch.d_info = h->d_info; ch.info_vec = info_vec;
+    ch.dinv = f.dinv; ch.logd = f.logd; ch.d_info = h->d_info; ch.aux = h->aux_stream; ch.ev = h->ev; ch.info_vec = info_vec;
     if (launch_potrf(s, ch)) return mfgp_fail(h, MFGP_ERR_CUDA, "potrf launch failed");
     if (launch_trtri(s, ch, f.W, f.ld, f.strideM, f.G)) return mfgp_fail(h, MFGP_ERR_CUDA, "trtri launch failed");
 

@@ -350,7 +350,7 @@ int svgp_forward(mfgp_handle* h, Scope& sc, int L, int M, int B, int d, double j
 
     CholArgs ch{};
     ch.A = f.Kmm; ch.N = M; ch.lda = f.ldM; ch.strideA = f.sMM; ch.batch = L;
-    ch.dinv = f.dinv; ch.logd = f.logd; ch.d_info = h->d_info; ch.info_vec = nullptr;
+    ch.dinv = f.dinv; ch.logd = f.logd; ch.d_info = h->d_info; ch.aux = h->aux_stream; ch.ev = h->ev; ch.info_vec = nullptr;
     if (launch_potrf(s, ch)) return mfgp_fail(h, MFGP_ERR_CUDA, "svgp: potrf failed");
     if (launch_trtri(s, ch, f.Wm, f.ldM, f.sMM, f.S)) return mfgp_fail(h, MFGP_ERR_CUDA, "svgp: trtri failed");
 

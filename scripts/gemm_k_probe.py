@@ -1,0 +1,26 @@
+"""GEMM efficiency vs K (rank-k update shapes of the blocked Cholesky)."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from multi_fidelity_gpflow_b200 import _lib
+
+dev = torch.device("cuda:0")
+h = _lib.Handle(0)
+s = torch.cuda.Stream(); torch.cuda.set_stream(s); h.set_stream(s.cuda_stream); h.set_async(True)
+n = 8192
+C = torch.zeros(n, n, dtype=torch.float64, device=dev)
+for K in (128, 256, 512, 1024, 4096):
+    A = torch.randn(n, K, dtype=torch.float64, device=dev)
+    for beta in (0.0, 1.0):
+        def run():
+            rc = _lib._lib.mfgp_gemm(h._h, b"N", b"T", n, n, K, -1.0, _lib._ptr(A), K, _lib._ptr(A), K, beta, _lib._ptr(C), n)
+            assert rc == 0
+        for _ in range(2): run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(5): run()
+        e1.record(s); torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) * 1e-3 / 5
+        tiles = (n // 128) ** 2
+        print(f"K={K:5d} beta={beta}: {t*1e3:8.3f} ms  {2*n*n*K/t/1e12:6.2f} TF  per-wave {t*1e6/(tiles/148):6.1f} us", flush=True)
