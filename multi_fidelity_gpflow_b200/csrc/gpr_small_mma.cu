@@ -24,8 +24,7 @@
 
 namespace {
 
-constexpr int WPC = 2;          // warps (= problems) per CTA
-constexpr int CTAS_PER_SM = 5;  // 10 warps / SM: register cap 204, ~22 KB shared memory per warp
+constexpr int WPC = 4;  // warps (= problems) per CTA
 constexpr double LOG2PI = 1.8378770664093454835606594728112;
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -111,13 +110,14 @@ __device__ __forceinline__ double fexp(double x) {
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
-template <int NT, int DMAX>
-__global__ void __launch_bounds__(WPC * 32, CTAS_PER_SM) gpr_small_mma_kernel(SmallArgs p, size_t warp_doubles) {
+template <int NT>
+__global__ void __launch_bounds__(WPC * 32) gpr_small_mma_kernel(SmallArgs p, size_t warp_doubles) {
     constexpr int NP = 8 * NT;
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int prob = blockIdx.x * WPC + warp;
-    if (prob >= p.B) return;  // whole warp exits together; no block-level barriers are used
+    const int prob_raw = blockIdx.x * WPC + warp;
+    const bool active = prob_raw < p.B;
+    const int prob = active ? prob_raw : p.B - 1;  // idle warps shadow the last problem (keeps __syncthreads legal)
     const int N = p.N, d = p.d;
     WarpMem<NT> m(smem + (size_t)warp * warp_doubles, d);
     Lane L;
@@ -179,98 +179,91 @@ __global__ void __launch_bounds__(WPC * 32, CTAS_PER_SM) gpr_small_mma_kernel(Sm
     double logdet2 = 0.0;  // sum log(pivot) = 2 sum log L_ii
 
     // =============================== phases A + B ================================================
-    // kb is a RUNTIME loop (code size: the fully unrolled version was 320 KB of SASS and ran out of the
-    // instruction cache); the tile-row index i stays compile-time so accumulators live in registers,
-    // guarded by warp-uniform predicates.
-#pragma unroll 1
+#pragma unroll
     for (int kb = 0; kb < NT; ++kb) {
+        __syncthreads();  // instruction-stream re-alignment (I-cache sharing)
         double acc[NT][2];
-        const int c0 = 8 * kb + 2 * t;
         // ---- assemble block column kb: tiles (i, kb), i >= kb ------------------------------------
         {
             double e[NT][2];
 #pragma unroll
-            for (int i = 0; i < NT; ++i) e[i][0] = e[i][1] = 0.0;
+            for (int i = kb; i < NT; ++i) e[i][0] = e[i][1] = 0.0;
             for (int q = 0; q < d; ++q) {
-                const double2 xc = *reinterpret_cast<const double2*>(m.xL + q * NP + c0);
+                const double2 xc = *reinterpret_cast<const double2*>(m.xL + q * NP + 8 * kb + 2 * t);
 #pragma unroll
-                for (int i = 0; i < NT; ++i)
-                    if (i >= kb) {
-                        const double xr = m.xL[q * NP + 8 * i + g];
-                        e[i][0] = fma(xr, xc.x, e[i][0]);
-                        e[i][1] = fma(xr, xc.y, e[i][1]);
-                    }
+                for (int i = kb; i < NT; ++i) {
+                    const double xr = m.xL[q * NP + 8 * i + g];
+                    e[i][0] = fma(xr, xc.x, e[i][0]);
+                    e[i][1] = fma(xr, xc.y, e[i][1]);
+                }
             }
+            const int c0 = 8 * kb + 2 * t;
             const double2 hc = *reinterpret_cast<const double2*>(m.hL + c0);
             const double2 sc = *reinterpret_cast<const double2*>(m.sv + c0);
 #pragma unroll
-            for (int i = 0; i < NT; ++i)
-                if (i >= kb) {
-                    const int r = 8 * i + g;
-                    const double hr = m.hL[r], sr = m.sv[r];
-                    acc[i][0] = (sr * sc.x) * vL * fexp(e[i][0] + (hr + hc.x));
-                    acc[i][1] = (sr * sc.y) * vL * fexp(e[i][1] + (hr + hc.y));
-                }
+            for (int i = kb; i < NT; ++i) {
+                const int r = 8 * i + g;
+                const double hr = m.hL[r], sr = m.sv[r];
+                acc[i][0] = (sr * sc.x) * vL * fexp(e[i][0] + (hr + hc.x));
+                acc[i][1] = (sr * sc.y) * vL * fexp(e[i][1] + (hr + hc.y));
+            }
             if ((hmask >> kb) & 1u) {  // this block column has HF points: add the discrepancy GP on HF x HF
 #pragma unroll
-                for (int i = 0; i < NT; ++i) e[i][0] = e[i][1] = 0.0;
+                for (int i = kb; i < NT; ++i) e[i][0] = e[i][1] = 0.0;
                 for (int q = 0; q < d; ++q) {
-                    const double2 xc = *reinterpret_cast<const double2*>(m.xD + q * NP + c0);
+                    const double2 xc = *reinterpret_cast<const double2*>(m.xD + q * NP + 8 * kb + 2 * t);
 #pragma unroll
-                    for (int i = 0; i < NT; ++i)
-                        if (i >= kb && ((hmask >> i) & 1u)) {
-                            const double xr = m.xD[q * NP + 8 * i + g];
-                            e[i][0] = fma(xr, xc.x, e[i][0]);
-                            e[i][1] = fma(xr, xc.y, e[i][1]);
-                        }
+                    for (int i = kb; i < NT; ++i) {
+                        const double xr = m.xD[q * NP + 8 * i + g];
+                        e[i][0] = fma(xr, xc.x, e[i][0]);
+                        e[i][1] = fma(xr, xc.y, e[i][1]);
+                    }
                 }
                 const double2 hdc = *reinterpret_cast<const double2*>(m.hD + c0);
                 const double2 hvc = *reinterpret_cast<const double2*>(m.hv + c0);
 #pragma unroll
-                for (int i = 0; i < NT; ++i)
-                    if (i >= kb && ((hmask >> i) & 1u)) {
-                        const int r = 8 * i + g;
-                        const double hr = m.hD[r], hvr = m.hv[r];
-                        acc[i][0] += (hvr * hvc.x) * vD * fexp(e[i][0] + (hr + hdc.x));
-                        acc[i][1] += (hvr * hvc.y) * vD * fexp(e[i][1] + (hr + hdc.y));
-                    }
+                for (int i = kb; i < NT; ++i) {
+                    if (!((hmask >> i) & 1u)) continue;
+                    const int r = 8 * i + g;
+                    const double hr = m.hD[r], hvr = m.hv[r];
+                    if (hvr * hvc.x != 0.0) acc[i][0] += vD * fexp(e[i][0] + (hr + hdc.x));
+                    if (hvr * hvc.y != 0.0) acc[i][1] += vD * fexp(e[i][1] + (hr + hdc.y));
+                }
             }
             // diagonal: + noise (real rows) or identity (padding rows keep the factorisation well posed)
-#pragma unroll
-            for (int i = 0; i < NT; ++i)
-                if (i == kb) {
-                    const int r = 8 * kb + g;
-                    if (r == c0) acc[i][0] += (r < N) ? noise : 1.0;
-                    if (r == c0 + 1) acc[i][1] += (r < N) ? noise : 1.0;
-                }
+            {
+                const int r = 8 * kb + g;
+                if (r == c0) acc[kb][0] += (r < N) ? noise : 1.0;
+                if (r == c0 + 1) acc[kb][1] += (r < N) ? noise : 1.0;
+            }
         }
         // ---- left-looking update: acc[i] -= sum_{k<kb} L_ik L_kbk^T ------------------------------
-#pragma unroll 1
+#pragma unroll
         for (int k = 0; k < kb; ++k) {
-            const double* tb = m.tiles + (kb * (kb + 1) / 2 + k) * 64;
+            const double* tb = m.tiles + slot(kb, k) * 64;
             const double b0 = tb[L.km[0]], b1 = tb[L.km[1]];
 #pragma unroll
-            for (int i = 0; i < NT; ++i)
-                if (i >= kb) {
-                    const double* ta = m.tiles + (i * (i + 1) / 2 + k) * 64;
-                    dmma(acc[i][0], acc[i][1], -ta[L.km[0]], b0);
-                    dmma(acc[i][0], acc[i][1], -ta[L.km[1]], b1);
-                }
-        }
-        // ---- publish the block column; factor the diagonal tile redundantly in registers ----------
-        double* td = m.tiles + (kb * (kb + 1) / 2 + kb) * 64;
-#pragma unroll
-        for (int i = 0; i < NT; ++i)
-            if (i >= kb) st_c(m.tiles + (i * (i + 1) / 2 + kb) * 64, L, acc[i][0], acc[i][1]);
-        __syncwarp();
-        double af0[NT], af1[NT];  // K-major fragments of the raw panel tiles (read before they are overwritten)
-#pragma unroll
-        for (int i = 0; i < NT; ++i)
-            if (i > kb) {
-                const double* ta = m.tiles + (i * (i + 1) / 2 + kb) * 64;
-                af0[i] = ta[L.km[0]];
-                af1[i] = ta[L.km[1]];
+            for (int i = kb; i < NT; ++i) {
+                const double* ta = m.tiles + slot(i, k) * 64;
+                const double a0 = (i == kb) ? b0 : ta[L.km[0]];
+                const double a1 = (i == kb) ? b1 : ta[L.km[1]];
+                dmma(acc[i][0], acc[i][1], -a0, b0);
+                dmma(acc[i][0], acc[i][1], -a1, b1);
             }
+        }
+        // ---- diagonal tile: publish, factor redundantly in registers, invert ---------------------
+        double* td = m.tiles + slot(kb, kb) * 64;
+        st_c(td, L, acc[kb][0], acc[kb][1]);
+#pragma unroll
+        for (int i = kb + 1; i < NT; ++i) st_c(m.tiles + slot(i, kb) * 64, L, acc[i][0], acc[i][1]);
+        __syncwarp();
+        double af0[NT], af1[NT];  // K-major fragments of the raw panel tiles (loaded before they are overwritten)
+#pragma unroll
+        for (int i = kb + 1; i < NT; ++i) {
+            const double* ta = m.tiles + slot(i, kb) * 64;
+            af0[i] = ta[L.km[0]];
+            af1[i] = ta[L.km[1]];
+        }
         {
             double a[8][8], rinv[8];
 #pragma unroll
@@ -314,106 +307,78 @@ __global__ void __launch_bounds__(WPC * 32, CTAS_PER_SM) gpr_small_mma_kernel(Sm
         }
         __syncwarp();
         // ---- panel: L_ik = A_ik inv(L_kk)^T -------------------------------------------------------
-        {
+        if (kb + 1 < NT) {
             const double wb0 = td[L.km[0]], wb1 = td[L.km[1]];
 #pragma unroll
-            for (int i = 0; i < NT; ++i)
-                if (i > kb) {
-                    double c0v = 0.0, c1v = 0.0;
-                    dmma(c0v, c1v, af0[i], wb0);
-                    dmma(c0v, c1v, af1[i], wb1);
-                    st_c(m.tiles + (i * (i + 1) / 2 + kb) * 64, L, c0v, c1v);
-                }
+            for (int i = kb + 1; i < NT; ++i) {
+                double c0 = 0.0, c1 = 0.0;
+                dmma(c0, c1, af0[i], wb0);
+                dmma(c0, c1, af1[i], wb1);
+                st_c(m.tiles + slot(i, kb) * 64, L, c0, c1);
+            }
         }
         __syncwarp();
     }
 
-    // =============================== phase C: W = L^-1 in place, one tile ROW at a time ==============
-    // T_ij = sum_{k=j}^{i-1} L_ik W_kj for every j < i (independent accumulator chains), then
-    // W_ij = -W_ii T_ij.  Row i only reads L tiles of row i and W tiles of rows < i.
-#pragma unroll 1
-    for (int i = 1; i < NT; ++i) {
-        double c[NT][2];
+    // =============================== phase C: W = L^-1 in place ===================================
 #pragma unroll
-        for (int j = 0; j < NT; ++j) c[j][0] = c[j][1] = 0.0;
-#pragma unroll 1
-        for (int k = 0; k < i; ++k) {
-            const double* ta = m.tiles + (i * (i + 1) / 2 + k) * 64;  // L_ik (K-major)
-            const double a0 = ta[L.km[0]], a1 = ta[L.km[1]];
+    for (int j = 0; j + 1 < NT; ++j) {
+        __syncthreads();
 #pragma unroll
-            for (int j = 0; j < NT - 1; ++j)
-                if (j <= k) {
-                    const double* tb = m.tiles + (k * (k + 1) / 2 + j) * 64;  // W_kj (M-major)
-                    dmma(c[j][0], c[j][1], a0, tb[L.mm[0]]);
-                    dmma(c[j][0], c[j][1], a1, tb[L.mm[1]]);
-                }
-        }
-        __syncwarp();
+        for (int i = j + 1; i < NT; ++i) {
+            double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-        for (int j = 0; j < NT - 1; ++j)
-            if (j < i) st_c(m.tiles + (i * (i + 1) / 2 + j) * 64, L, c[j][0], c[j][1]);
-        __syncwarp();
-        const double* tw = m.tiles + (i * (i + 1) / 2 + i) * 64;  // W_ii
-        const double w0 = -tw[L.km[0]], w1 = -tw[L.km[1]];
-#pragma unroll
-        for (int j = 0; j < NT - 1; ++j)
-            if (j < i) {
-                const double* tij = m.tiles + (i * (i + 1) / 2 + j) * 64;
-                c[j][0] = c[j][1] = 0.0;
-                dmma(c[j][0], c[j][1], w0, tij[L.mm[0]]);
-                dmma(c[j][0], c[j][1], w1, tij[L.mm[1]]);
+            for (int k = j; k < i; ++k) {
+                const double* ta = m.tiles + slot(i, k) * 64;  // L_ik (K-major: row g, col t+4s)
+                const double* tb = m.tiles + slot(k, j) * 64;  // W_kj (M-major: row t+4s, col g)
+                dmma(c0, c1, ta[L.km[0]], tb[L.mm[0]]);
+                dmma(c0, c1, ta[L.km[1]], tb[L.mm[1]]);
             }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < NT - 1; ++j)
-            if (j < i) st_c(m.tiles + (i * (i + 1) / 2 + j) * 64, L, c[j][0], c[j][1]);
-        __syncwarp();
+            double* tij = m.tiles + slot(i, j) * 64;
+            __syncwarp();
+            st_c(tij, L, c0, c1);  // T = sum_k L_ik W_kj  (L_ij itself is dead from here on)
+            __syncwarp();
+            const double* tw = m.tiles + slot(i, i) * 64;  // W_ii
+            double w0 = 0.0, w1 = 0.0;
+            dmma(w0, w1, -tw[L.km[0]], tij[L.mm[0]]);
+            dmma(w0, w1, -tw[L.km[1]], tij[L.mm[1]]);
+            __syncwarp();
+            st_c(tij, L, w0, w1);
+            __syncwarp();
+        }
     }
 
     // =============================== phase D: a = W y, alpha = W^T a, value ========================
-    {
-        double c[NT][2];
 #pragma unroll
-        for (int i = 0; i < NT; ++i) c[i][0] = c[i][1] = 0.0;
-#pragma unroll 1
-        for (int j = 0; j < NT; ++j) {
+    for (int i = 0; i < NT; ++i) {
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            const double* tw = m.tiles + slot(i, j) * 64;
             const double y0 = (g == 0) ? m.yv[8 * j + t] : 0.0, y1 = (g == 0) ? m.yv[8 * j + t + 4] : 0.0;
-#pragma unroll
-            for (int i = 0; i < NT; ++i)
-                if (i >= j) {
-                    const double* tw = m.tiles + (i * (i + 1) / 2 + j) * 64;
-                    dmma(c[i][0], c[i][1], tw[L.km[0]], y0);
-                    dmma(c[i][0], c[i][1], tw[L.km[1]], y1);
-                }
+            dmma(c0, c1, tw[L.km[0]], y0);
+            dmma(c0, c1, tw[L.km[1]], y1);
         }
-        if (t == 0) {
+        if (t == 0) m.av[8 * i + g] = c0;
+    }
+    __syncwarp();
 #pragma unroll
-            for (int i = 0; i < NT; ++i) m.av[8 * i + g] = c[i][0];
-        }
-        __syncwarp();
+    for (int j = 0; j < NT; ++j) {
+        double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-        for (int j = 0; j < NT; ++j) c[j][0] = c[j][1] = 0.0;
-#pragma unroll 1
-        for (int i = 0; i < NT; ++i) {
+        for (int i = j; i < NT; ++i) {
+            const double* tw = m.tiles + slot(i, j) * 64;  // A[m][k] = W_ij[k][m]
             const double a0 = (g == 0) ? m.av[8 * i + t] : 0.0, a1 = (g == 0) ? m.av[8 * i + t + 4] : 0.0;
-#pragma unroll
-            for (int j = 0; j < NT; ++j)
-                if (j <= i) {
-                    const double* tw = m.tiles + (i * (i + 1) / 2 + j) * 64;  // A[m][k] = W_ij[k][m]
-                    dmma(c[j][0], c[j][1], tw[L.mm[0]], a0);
-                    dmma(c[j][0], c[j][1], tw[L.mm[1]], a1);
-                }
+            dmma(c0, c1, tw[L.mm[0]], a0);
+            dmma(c0, c1, tw[L.mm[1]], a1);
         }
-        if (t == 0) {
-#pragma unroll
-            for (int j = 0; j < NT; ++j) m.al[8 * j + g] = c[j][0];
-        }
+        if (t == 0) m.al[8 * j + g] = c0;
     }
     {
         double q = 0.0;
         for (int r = lane; r < NP; r += 32) q = fma(m.av[r], m.av[r], q);
         q = warp_sum(q);
-        if (lane == 0) {
+        if (lane == 0 && active) {
             p.nlml[prob] = 0.5 * q + 0.5 * logdet2 + 0.5 * N * LOG2PI;
             if (p.info) p.info[prob] = bad;
             if (bad) atomicCAS(p.d_info, 0, bad);
@@ -423,100 +388,72 @@ __global__ void __launch_bounds__(WPC * 32, CTAS_PER_SM) gpr_small_mma_kernel(Sm
     __syncwarp();
 
     // =============================== phase E: K^-1, G, contraction ===================================
-    {
-        constexpr int NTRI = NT * (NT + 1) / 2;
-        double kacc[NTRI][2];
+    constexpr int NTRI = NT * (NT + 1) / 2;
+    double kacc[NTRI][2];
 #pragma unroll
-        for (int s = 0; s < NTRI; ++s) kacc[s][0] = kacc[s][1] = 0.0;
-#pragma unroll 1
-        for (int k = 0; k < NT; ++k) {
-            double f0[NT], f1[NT];
+    for (int s = 0; s < NTRI; ++s) kacc[s][0] = kacc[s][1] = 0.0;
 #pragma unroll
-            for (int i = 0; i < NT; ++i)
-                if (i <= k) {
-                    const double* tw = m.tiles + (k * (k + 1) / 2 + i) * 64;  // W_ki, M-major: A (W_ki^T) and B (W_kj)
-                    f0[i] = tw[L.mm[0]];
-                    f1[i] = tw[L.mm[1]];
-                }
+    for (int k = 0; k < NT; ++k) {
+        __syncthreads();
+        double f0[NT], f1[NT];
 #pragma unroll
-            for (int i = 0; i < NT; ++i)
-                if (i <= k) {
-#pragma unroll
-                    for (int j = 0; j <= i; ++j) {
-                        dmma(kacc[slot(i, j)][0], kacc[slot(i, j)][1], f0[i], f0[j]);
-                        dmma(kacc[slot(i, j)][0], kacc[slot(i, j)][1], f1[i], f1[j]);
-                    }
-                }
+        for (int i = 0; i <= k; ++i) {
+            const double* tw = m.tiles + slot(k, i) * 64;  // W_ki, M-major: serves as A (W_ki^T) and as B (W_kj)
+            f0[i] = tw[L.mm[0]];
+            f1[i] = tw[L.mm[1]];
         }
-        __syncwarp();  // W tiles are dead: the slots now receive K^-1
 #pragma unroll
-        for (int s = 0; s < NTRI; ++s) st_c(m.tiles + s * 64, L, kacc[s][0], kacc[s][1]);
+        for (int i = 0; i <= k; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                dmma(kacc[slot(i, j)][0], kacc[slot(i, j)][1], f0[i], f0[j]);
+                dmma(kacc[slot(i, j)][0], kacc[slot(i, j)][1], f1[i], f1[j]);
+            }
     }
-    __syncwarp();
+    __syncthreads();  // W tiles are dead: the slots are reused for G
     const int nq = 2 * d + 4;
     double s_vL = 0.0, s_rho = 0.0, s_dg = 0.0;
-    double sLq[DMAX];
 #pragma unroll
-    for (int q = 0; q < DMAX; ++q) sLq[q] = 0.0;
-#pragma unroll 1
     for (int j = 0; j < NT; ++j) {
+        __syncthreads();
         // K^L of block column j recomputed exactly as in the assembly (expanded-square form)
         double e[NT][2];
 #pragma unroll
-        for (int i = 0; i < NT; ++i) e[i][0] = e[i][1] = 0.0;
-        const int c0 = 8 * j + 2 * t;
+        for (int i = j; i < NT; ++i) e[i][0] = e[i][1] = 0.0;
         for (int q = 0; q < d; ++q) {
-            const double2 xc = *reinterpret_cast<const double2*>(m.xL + q * NP + c0);
+            const double2 xc = *reinterpret_cast<const double2*>(m.xL + q * NP + 8 * j + 2 * t);
 #pragma unroll
-            for (int i = 0; i < NT; ++i)
-                if (i >= j) {
-                    const double xr = m.xL[q * NP + 8 * i + g];
-                    e[i][0] = fma(xr, xc.x, e[i][0]);
-                    e[i][1] = fma(xr, xc.y, e[i][1]);
-                }
+            for (int i = j; i < NT; ++i) {
+                const double xr = m.xL[q * NP + 8 * i + g];
+                e[i][0] = fma(xr, xc.x, e[i][0]);
+                e[i][1] = fma(xr, xc.y, e[i][1]);
+            }
         }
+        const int c0 = 8 * j + 2 * t;
         const double2 hc = *reinterpret_cast<const double2*>(m.hL + c0);
         const double2 sc = *reinterpret_cast<const double2*>(m.sv + c0);
         const double2 hvc = *reinterpret_cast<const double2*>(m.hv + c0);
         const double2 alc = *reinterpret_cast<const double2*>(m.al + c0);
 #pragma unroll
-        for (int i = 0; i < NT; ++i)
-            if (i >= j) {
-                const int r = 8 * i + g;
-                double* tg = m.tiles + (i * (i + 1) / 2 + j) * 64;
-                const double2 kinv = *reinterpret_cast<const double2*>(tg + L.cst);
-                const double hr = m.hL[r], sr = m.sv[r], hvr = m.hv[r], alr = m.al[r];
-                double g0 = alr * alc.x - kinv.x, g1 = alr * alc.y - kinv.y;
-                // multiplicity: lower triangle twice, diagonal once, padding / upper part of diagonal tiles zero
-                double w0 = (c0 < r) ? 2.0 : (c0 == r ? 1.0 : 0.0), w1 = (c0 + 1 < r) ? 2.0 : (c0 + 1 == r ? 1.0 : 0.0);
-                if (r >= N) w0 = w1 = 0.0;
-                g0 *= w0;
-                g1 *= w1;
-                st_c(tg, L, g0, g1);  // weighted G (read by the HF x HF pass); same lane, same address as the load
-                if (c0 == r) s_dg += g0;
-                if (c0 + 1 == r) s_dg += g1;
-                const double t0 = g0 * ((sr * sc.x) * vL * fexp(e[i][0] + (hr + hc.x)));  // T^L = w G K^L
-                const double t1 = g1 * ((sr * sc.y) * vL * fexp(e[i][1] + (hr + hc.y)));
-                e[i][0] = t0;
-                e[i][1] = t1;
-                s_vL += t0 + t1;
-                s_rho += t0 * (hvr + hvc.x) + t1 * (hvr + hvc.y);
-            }
-#pragma unroll
-        for (int q = 0; q < DMAX; ++q)
-            if (q < d) {
-                const double2 xc = *reinterpret_cast<const double2*>(m.xL + q * NP + c0);
-                double acc_q = sLq[q];
-#pragma unroll
-                for (int i = 0; i < NT; ++i)
-                    if (i >= j) {
-                        const double xr = m.xL[q * NP + 8 * i + g];
-                        const double d0 = xr - xc.x, d1 = xr - xc.y;
-                        acc_q = fma(e[i][0] * d0, d0, acc_q);
-                        acc_q = fma(e[i][1] * d1, d1, acc_q);
-                    }
-                sLq[q] = acc_q;
-            }
+        for (int i = j; i < NT; ++i) {
+            const int r = 8 * i + g;
+            const double hr = m.hL[r], sr = m.sv[r], hvr = m.hv[r], alr = m.al[r];
+            double g0 = alr * alc.x - kacc[slot(i, j)][0], g1 = alr * alc.y - kacc[slot(i, j)][1];
+            // multiplicity: lower triangle counted twice, diagonal once, (padding / upper part of diagonal tiles) zero
+            double w0 = (c0 < r) ? 2.0 : (c0 == r ? 1.0 : 0.0), w1 = (c0 + 1 < r) ? 2.0 : (c0 + 1 == r ? 1.0 : 0.0);
+            if (r >= N) w0 = w1 = 0.0;
+            g0 *= w0;
+            g1 *= w1;
+            st_c(m.tiles + slot(i, j) * 64, L, g0, g1);  // weighted G (read by the HF x HF pass)
+            if (c0 == r) s_dg += g0;
+            if (c0 + 1 == r) s_dg += g1;
+            const double t0 = g0 * ((sr * sc.x) * vL * fexp(e[i][0] + (hr + hc.x)));
+            const double t1 = g1 * ((sr * sc.y) * vL * fexp(e[i][1] + (hr + hc.y)));
+            kacc[slot(i, j)][0] = t0;  // T^L = w G K^L
+            kacc[slot(i, j)][1] = t1;
+            s_vL += t0 + t1;
+            s_rho += t0 * (hvr + hvc.x) + t1 * (hvr + hvc.y);
+        }
     }
     {
         const double a0 = warp_sum(s_rho), a1 = warp_sum(s_vL), a2 = warp_sum(s_dg);
@@ -525,12 +462,22 @@ __global__ void __launch_bounds__(WPC * 32, CTAS_PER_SM) gpr_small_mma_kernel(Sm
             m.red[1 + d] = a1;
             m.red[3 + 2 * d] = a2;
         }
+    }
+    for (int q = 0; q < d; ++q) {
+        double sL = 0.0;
 #pragma unroll
-        for (int q = 0; q < DMAX; ++q)
-            if (q < d) {
-                const double sL = warp_sum(sLq[q]);
-                if (lane == 0) m.red[1 + q] = sL;
+        for (int j = 0; j < NT; ++j) {
+            const double2 xc = *reinterpret_cast<const double2*>(m.xL + q * NP + 8 * j + 2 * t);
+#pragma unroll
+            for (int i = j; i < NT; ++i) {
+                const double xr = m.xL[q * NP + 8 * i + g];
+                const double d0 = xr - xc.x, d1 = xr - xc.y;
+                sL = fma(kacc[slot(i, j)][0] * d0, d0, sL);
+                sL = fma(kacc[slot(i, j)][1] * d1, d1, sL);
             }
+        }
+        sL = warp_sum(sL);
+        if (lane == 0) m.red[1 + q] = sL;
     }
     __syncwarp();  // weighted G tiles visible to all lanes
     {
@@ -546,9 +493,9 @@ __global__ void __launch_bounds__(WPC * 32, CTAS_PER_SM) gpr_small_mma_kernel(Sm
             double ee = m.hD[i] + m.hD[j];
             for (int q = 0; q < d; ++q) ee = fma(m.xD[q * NP + i], m.xD[q * NP + j], ee);
             double* gp = m.tiles + slot(i >> 3, j >> 3) * 64 + tile_off(i & 7, j & 7);
-            const double tdv = (*gp) * vD * fexp(ee);
-            *gp = tdv;
-            s_vD += tdv;
+            const double td = (*gp) * vD * fexp(ee);
+            *gp = td;
+            s_vD += td;
         }
         s_vD = warp_sum(s_vD);
         if (lane == 0) m.red[2 + 2 * d] = s_vD;
@@ -569,7 +516,7 @@ __global__ void __launch_bounds__(WPC * 32, CTAS_PER_SM) gpr_small_mma_kernel(Sm
         }
     }
     __syncwarp();
-    for (int q = lane; q < nq; q += 32) {
+    for (int q = lane; q < nq && active; q += 32) {
         double f = 1.0;
         if (q == 0) f = 1.0 / rho;
         else if (q <= d) f = m.th[2 * d + 3 + (q - 1)];
@@ -580,22 +527,18 @@ __global__ void __launch_bounds__(WPC * 32, CTAS_PER_SM) gpr_small_mma_kernel(Sm
     }
 }
 
-template <int NT, int DMAX>
-int launch_nt_d(cudaStream_t st, const SmallArgs& a) {
+template <int NT>
+int launch_nt(cudaStream_t st, const SmallArgs& a) {
     const size_t wd = (WarpMem<NT>::doubles(a.d) + 1) & ~(size_t)1;  // keep every warp's base 16-byte aligned
     const size_t bytes = wd * 8 * WPC;
     static int attr_bytes = 0;
     if ((int)bytes > attr_bytes) {
-        if (cudaFuncSetAttribute(gpr_small_mma_kernel<NT, DMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+        if (cudaFuncSetAttribute(gpr_small_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
             return -2;
         attr_bytes = (int)bytes;
     }
-    gpr_small_mma_kernel<NT, DMAX><<<(a.B + WPC - 1) / WPC, WPC * 32, bytes, st>>>(a, wd);
+    gpr_small_mma_kernel<NT><<<(a.B + WPC - 1) / WPC, WPC * 32, bytes, st>>>(a, wd);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
-}
-template <int NT>
-int launch_nt(cudaStream_t st, const SmallArgs& a) {
-    return a.d <= 8 ? launch_nt_d<NT, 8>(st, a) : launch_nt_d<NT, 16>(st, a);
 }
 
 }  // namespace

@@ -1,0 +1,66 @@
+"""Multi-GPU tests (skipped unless >= 2 CUDA devices): data-parallel SVGP over NCCL equals the single-GPU
+result; sharded bins equal the unsharded batch."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, json
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from multi_fidelity_gpflow_b200 import _lib
+from multi_fidelity_gpflow_b200.dist import dp_svgp_value_and_grad, gather_bins, shard_range
+from oracle import mfgp_oracle as onp
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+h = _lib.Handle(rank)
+ds = onp.load_dataset("hbs")
+X, Y = ds["X"], ds["Y"]
+rng = np.random.default_rng(0)
+B = Y.shape[1]
+th = np.tile(onp.default_theta(5), (B, 1)) * np.exp(0.1 * rng.standard_normal((B, 13)))
+nz = np.full(B, 1e-3)
+lo, hi = shard_range(B, rank, world)
+nl, gr = h.gpr_batched_nlml_grad(X, np.ascontiguousarray(Y[:, lo:hi]), th[lo:hi], nz[lo:hi])
+full_n, full_g = gather_bins(nl, B), gather_bins(gr, B)
+M, L, P = 50, 10, 49
+W = onp.initialize_W(P, L, 0.4, 0.2)
+ths = np.tile(onp.default_theta(5), (L, 1))
+q_mu, q_sqrt = 0.1 * rng.standard_normal((M, L)), np.tile(0.3 * np.eye(M), (L, 1, 1))
+Z = ds["Z_kmeans50"]
+fn = lambda Xr, Yr, scale, klm: h.svgp_elbo_grad(Xr, Yr, Z, ths, W, q_mu, q_sqrt, 0.8, scale=scale, kl_mult=klm)
+out = dp_svgp_value_and_grad(fn, X, Y, num_data=53, kl_mult=1.3)
+if rank == 0:
+    ref_n, ref_g = h.gpr_batched_nlml_grad(X, Y, th, nz)
+    ref = h.svgp_elbo_grad(X, Y, Z, ths, W, q_mu, q_sqrt, 0.8, scale=1.0, kl_mult=1.3)
+    ok = bool(np.array_equal(full_n, ref_n) and np.array_equal(full_g, ref_g))
+    err = {k: float(np.max(np.abs(np.asarray(out[k]) - np.asarray(ref[k]))) / (np.max(np.abs(np.asarray(ref[k]))) + 1e-300))
+           for k in ("g_Z", "g_thetas", "g_q_mu", "g_q_sqrt", "g_W", "g_lik_var", "elbo")}
+    print("RESULT " + json.dumps({"bins_bit_identical": ok, "err": err}))
+dist.destroy_process_group()
+''' % ROOT
+
+
+def test_two_gpu_sharding_and_dp_svgp(tmp_path):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29631", str(script)], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    import json
+
+    line = [l for l in res.stdout.splitlines() if l.startswith("RESULT ")][0]
+    r = json.loads(line[7:])
+    assert r["bins_bit_identical"]
+    assert all(v < 1e-10 for v in r["err"].values()), r
