@@ -64,3 +64,47 @@ def test_two_gpu_sharding_and_dp_svgp(tmp_path):
     r = json.loads(line[7:])
     assert r["bins_bit_identical"]
     assert all(v < 1e-10 for v in r["err"].values()), r
+
+
+CHOL_WORKER = r"""
+import os, sys, json
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from multi_fidelity_gpflow_b200 import _lib
+from multi_fidelity_gpflow_b200.dist_chol import distributed_gpr_nlml
+from oracle import mfgp_oracle as onp
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+h = _lib.Handle(rank)
+res = {}
+for N, nbd in ((1500, 256), (2048, 512)):
+    ds = onp.synthetic_exact_dataset(N)
+    v = distributed_gpr_nlml(h, ds["X"], ds["Y"], ds["theta"], ds["noise"], nbd=nbd)
+    if rank == 0:
+        h.set_stream(None)
+        single = h.gpr_nlml(ds["X"], ds["Y"], ds["theta"], ds["noise"])
+        ref = -onp.gpr_lml(ds["X"], ds["Y"], ds["theta"], ds["noise"])
+        res[N] = [v, single, ref]
+if rank == 0:
+    print("RESULT " + json.dumps(res))
+dist.destroy_process_group()
+""" % ROOT
+
+
+def test_two_gpu_distributed_cholesky_nlml(tmp_path):
+    import json
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "chol_worker.py"
+    script.write_text(CHOL_WORKER)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29632", str(script)], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    r = json.loads([l for l in res.stdout.splitlines() if l.startswith("RESULT ")][0][7:])
+    for N, (v, single, ref) in r.items():
+        assert abs(v - ref) < 1e-9 * abs(ref), (N, v, ref)
+        assert abs(v - single) < 1e-9 * abs(single)
