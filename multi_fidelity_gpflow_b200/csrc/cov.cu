@@ -15,6 +15,8 @@
 // (column segments) are written as full 128-byte lines with 128-bit STG.
 #include "cov.cuh"
 
+#include "mathx.cuh"
+
 #include <cstdio>
 
 namespace {
@@ -159,7 +161,7 @@ __device__ inline void tile_index(long t, int TJ, int symmetric, int& I, int& J)
     }
 }
 
-__global__ void __launch_bounds__(256) cov_kernel(CovArgs p, int TJ, int vec_ok) {
+__global__ void __launch_bounds__(256, 2) cov_kernel(CovArgs p, int TJ, int vec_ok) {
     extern __shared__ __align__(16) double smem[];
     const TileSmem t = carve(smem, p.d);
     int I, J;
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(256) cov_kernel(CovArgs p, int TJ, int vec_ok)
         for (int c = 0; c < 4; ++c) {
             const int cc = col_of(tx, c);
             // (s_a s_b) and (h_a + h_b) are commutative: K(X,X) comes out exactly symmetric
-            val[a][c] = (t.fa[r0 + a] * t.sb[cc]) * vL * exp(acc[a][c] + (t.haL[r0 + a] + t.hbL[cc]));
+            val[a][c] = (t.fa[r0 + a] * t.sb[cc]) * vL * fexp(acc[a][c] + (t.haL[r0 + a] + t.hbL[cc]));
         }
     if (t.flags[0] && t.flags[1]) {  // tile touches the HF x HF block: add the discrepancy GP
         tile_dots(t.aD, t.bD, p.d, r0, tx, acc);
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(256) cov_kernel(CovArgs p, int TJ, int vec_ok)
             for (int c = 0; c < 4; ++c) {
                 const int cc = col_of(tx, c);
                 const double g = t.ga[r0 + a] * t.hb[cc];
-                if (g != 0.0) val[a][c] += g * exp(acc[a][c] + (t.haD[r0 + a] + t.hbD[cc]));
+                if (g != 0.0) val[a][c] += g * fexp(acc[a][c] + (t.haD[r0 + a] + t.hbD[cc]));
             }
     }
     if (p.symmetric && I == J) {
@@ -264,7 +266,7 @@ __device__ inline double warp_sum(double v) {
 }
 
 template <bool ROWGRAD>
-__global__ void __launch_bounds__(256) cov_grad_kernel(CovGradArgs p, int TJ, long ntiles) {
+__global__ void __launch_bounds__(256, 2) cov_grad_kernel(CovGradArgs p, int TJ, long ntiles) {
     extern __shared__ __align__(16) double smem[];
     const int d = p.d;
     const TileSmem t = carve(smem, d);
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(256) cov_grad_kernel(CovGradArgs p, int TJ, lo
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int cc = col_of(tx, c);
-            const double kl = (t.fa[r0 + a] * t.sb[cc]) * vL * exp(acc[a][c] + (t.haL[r0 + a] + t.hbL[cc]));
+            const double kl = (t.fa[r0 + a] * t.sb[cc]) * vL * fexp(acc[a][c] + (t.haL[r0 + a] + t.hbL[cc]));
             const double v = TL[a][c] * kl;  // G_ij * K^L_ij
             TL[a][c] = v;
             s_vL += v;
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(256) cov_grad_kernel(CovGradArgs p, int TJ, lo
             for (int c = 0; c < 4; ++c) {
                 const int cc = col_of(tx, c);
                 const double g = t.ga[r0 + a] * t.hb[cc];
-                const double v = (g != 0.0) ? TD[a][c] * g * exp(acc[a][c] + (t.haD[r0 + a] + t.hbD[cc])) : 0.0;
+                const double v = (g != 0.0) ? TD[a][c] * g * fexp(acc[a][c] + (t.haD[r0 + a] + t.hbD[cc])) : 0.0;
                 TD[a][c] = v;
                 s_vD += v;
             }

@@ -6,7 +6,8 @@
 // laid out so that the three access patterns a DMMA fragment needs are bank-conflict free:
 //   C-fragment store (row g, cols 2t,2t+1 -> one STS.128), K-major fragment (row g, col t+4s) and
 //   M-major fragment (row t+4s, col g):   byte(r, c) = r*64 + (((c>>1) ^ (r&2)) << 4) + ((c&1) << 3).
-// No __syncthreads anywhere: a warp owns its problem, so only __syncwarp orders its smem traffic.
+// A warp owns its problem, so only __syncwarp orders its smem traffic; the few __syncthreads keep the
+// 4 warps of a CTA (identical instruction streams) in step so they share instruction-cache lines.
 //
 //   A+B  left-looking blocked Cholesky; block column kb is ASSEMBLED on the fly into DMMA accumulators
 //        (fused MF kernel, expanded-square distance + exp), updated with sum_k L_ik L_kbk^T (DMMA), the
@@ -21,10 +22,11 @@
 #include <cstdint>
 
 #include "gpr_small.cuh"
+#include "mathx.cuh"
 
 namespace {
 
-constexpr int WPC = 4;  // warps (= problems) per CTA
+constexpr int WPC = 4;  // warps (= problems) per CTA (2 CTAs per SM; 3x3 and 5x2 were measured slower)
 constexpr double LOG2PI = 1.8378770664093454835606594728112;
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -83,32 +85,6 @@ struct WarpMem {
         hidx = reinterpret_cast<int*>(red + 2 * d + 4);
     }
 };
-
-// Branch-free exp for arguments <= ~0 (the SE kernel exponent): round-to-nearest range reduction,
-// degree-13 Taylor/Horner on |r| <= ln2/2 (truncation 4e-18), exponent spliced into the high word.
-__device__ __forceinline__ double fexp(double x) {
-    x = fmax(x, -700.0);
-    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
-    const int n = __double2loint(t);
-    const double nf = t - 6755399441055744.0;
-    double r = fma(nf, -6.93147180369123816490e-01, x);
-    r = fma(nf, -1.90821492927058770002e-10, r);
-    double p = 1.6059043836821613e-10;            // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);          // 1/12!
-    p = fma(p, r, 2.505210838544172e-08);         // 1/11!
-    p = fma(p, r, 2.755731922398589e-07);         // 1/10!
-    p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
-    p = fma(p, r, 2.48015873015873e-05);          // 1/8!
-    p = fma(p, r, 1.984126984126984e-04);         // 1/7!
-    p = fma(p, r, 1.388888888888889e-03);         // 1/6!
-    p = fma(p, r, 8.333333333333333e-03);         // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
-}
 
 template <int NT>
 __global__ void __launch_bounds__(WPC * 32) gpr_small_mma_kernel(SmallArgs p, size_t warp_doubles) {
