@@ -113,7 +113,8 @@ int mfgp_svgp_predict(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* Xs
  * Runs the DMMA (mma.sync m8n8k4 f64) tile kernel. */
 int mfgp_gemm(mfgp_handle* h, char transa, char transb, int m, int n, int k, double alpha,
               const double* A, long lda, const double* B, long ldb, double beta, double* C, long ldc);
-/* In-place lower Cholesky A = L L^T (row-major, strictly-upper part zeroed on return). */
+/* In-place lower Cholesky A = L L^T (row-major).  Only the lower triangle is referenced; on return the
+ * strictly-upper part of every 128x128 diagonal block is zeroed, upper off-diagonal blocks are untouched. */
 int mfgp_potrf(mfgp_handle* h, double* A, int N, long lda);
 /* Winv [N, N] = inv(L) for the lower factor produced by mfgp_potrf. */
 int mfgp_potrf_inv(mfgp_handle* h, double* A, int N, long lda, double* Winv, long ldw);

@@ -66,49 +66,87 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) potrf_diag_kernel(DiagArgs p)
     if (tid == 0) bad = 0;
 
     // ---- load the lower triangle into tiles; pad with identity up to a multiple of 8 ---------------
+    // 128-bit loads, 8 in flight per thread (a load->store chain per element exposed one L2/DRAM round trip
+    // per iteration: 77k of the kernel's 237k cycles in the first profile).
     for (int idx = tid; idx < ntb * (ntb + 1) / 2 * 64; idx += DIAG_THREADS) Lt[idx] = 0.0;
     __syncthreads();
-    for (int idx = tid; idx < nb * NB; idx += DIAG_THREADS) {
-        const int r = idx >> 7, c = idx & (NB - 1);
-        if (c <= r) Lt[tslot(r >> 3, c >> 3) * 64 + tile_off(r & 7, c & 7)] = A[(long)r * p.lda + c];
+    {
+        const bool vec = ((reinterpret_cast<size_t>(A) & 15) == 0) && ((p.lda & 1) == 0);
+        constexpr int UN = 8;
+        for (int base = 0; base < nb * (NB / 2); base += DIAG_THREADS * UN) {
+            double2 v[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int idx = base + u * DIAG_THREADS + tid;
+                const int r = idx >> 6, c = (idx & 63) * 2;
+                v[u] = make_double2(0.0, 0.0);
+                if (r < nb && c <= r) {
+                    const double* src = A + (long)r * p.lda + c;
+                    if (vec) v[u] = *reinterpret_cast<const double2*>(src);
+                    else {
+                        v[u].x = src[0];
+                        if (c + 1 <= r) v[u].y = src[1];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int idx = base + u * DIAG_THREADS + tid;
+                const int r = idx >> 6, c = (idx & 63) * 2;
+                if (r < nb && c <= r) {
+                    if (c + 1 > r) v[u].y = 0.0;  // strictly-upper element of a diagonal tile
+                    *reinterpret_cast<double2*>(Lt + tslot(r >> 3, c >> 3) * 64 + tile_off(r & 7, c & 7)) = v[u];
+                }
+            }
+        }
     }
     for (int r = nb + tid; r < ntb * 8; r += DIAG_THREADS) Lt[tslot(r >> 3, r >> 3) * 64 + tile_off(r & 7, r & 7)] = 1.0;
     __syncthreads();
 
-#pragma unroll 1
-    for (int kb = 0; kb < ntb; ++kb) {
-        // ---- update block column kb: tile (i, kb) -= sum_{k<kb} L_ik L_kbk^T, rows i = kb + warp + 4s --------
-        {
+    // Left-looking with a one-column look-ahead: while warp 0 factors the 8x8 diagonal tile of column kb
+    // (a ~2k-cycle dependent chain), warps 1-3 already apply the terms k < kb to column kb+1; only the last
+    // term (k = kb) of each column sits on the critical path.
+    auto update_tiles = [&](int col, int kfrom, int kto, int w, int nw) {
+        // tile (i, col) -= sum_{k=kfrom}^{kto-1} L_ik L_col,k^T for rows i = col + w, col + w + nw, ... (4 chains per pass)
+        for (int ibase = col + w; ibase < ntb; ibase += 4 * nw) {
             double acc[4][2];
             int row[4];
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                row[s] = kb + warp + 4 * s;
-                if (row[s] < ntb) {
-                    const double2 v = *reinterpret_cast<const double2*>(Lt + tslot(row[s], kb) * 64 + cst);
-                    acc[s][0] = v.x;
-                    acc[s][1] = v.y;
+            for (int s4 = 0; s4 < 4; ++s4) {
+                row[s4] = ibase + s4 * nw;
+                if (row[s4] < ntb) {
+                    const double2 v = *reinterpret_cast<const double2*>(Lt + tslot(row[s4], col) * 64 + cst);
+                    acc[s4][0] = v.x;
+                    acc[s4][1] = v.y;
                 }
             }
 #pragma unroll 1
-            for (int k = 0; k < kb; ++k) {
-                const double* tb = Lt + tslot(kb, k) * 64;
+            for (int k = kfrom; k < kto; ++k) {
+                const double* tb = Lt + tslot(col, k) * 64;
                 const double b0 = tb[km0], b1 = tb[km1];
 #pragma unroll
-                for (int s = 0; s < 4; ++s)
-                    if (row[s] < ntb) {
-                        const double* ta = Lt + tslot(row[s], k) * 64;
-                        dmma(acc[s][0], acc[s][1], -ta[km0], b0);
-                        dmma(acc[s][0], acc[s][1], -ta[km1], b1);
+                for (int s4 = 0; s4 < 4; ++s4)
+                    if (row[s4] < ntb) {
+                        const double* ta = Lt + tslot(row[s4], k) * 64;
+                        dmma(acc[s4][0], acc[s4][1], -ta[km0], b0);
+                        dmma(acc[s4][0], acc[s4][1], -ta[km1], b1);
                     }
             }
 #pragma unroll
-            for (int s = 0; s < 4; ++s)
-                if (row[s] < ntb) *reinterpret_cast<double2*>(Lt + tslot(row[s], kb) * 64 + cst) = make_double2(acc[s][0], acc[s][1]);
+            for (int s4 = 0; s4 < 4; ++s4)
+                if (row[s4] < ntb)
+                    *reinterpret_cast<double2*>(Lt + tslot(row[s4], col) * 64 + cst) = make_double2(acc[s4][0], acc[s4][1]);
         }
+    };
+#pragma unroll 1
+    for (int kb = 0; kb < ntb; ++kb) {
+        // ---- finish column kb: only the term k = kb-1 is still missing (earlier terms were applied one step ahead)
+        if (kb > 0) update_tiles(kb, kb - 1, kb, warp, 4);
         __syncthreads();
-        // ---- diagonal tile: redundant register Cholesky + inverse by the first warp ----------------------
-        if (warp == 0) {
+        // ---- warp 0: diagonal tile (redundant register Cholesky + inverse); warps 1-3: look-ahead on column kb+1
+        if (warp != 0) {
+            if (kb + 1 < ntb && kb > 0) update_tiles(kb + 1, 0, kb, warp - 1, 3);
+        } else {
             double* td = Lt + tslot(kb, kb) * 64;
             double* tw = Wt + tslot(kb, kb) * 64;
             double a[8][8], rinv[8];
@@ -265,82 +303,88 @@ int launch_potrf(cudaStream_t s, const CholArgs& a) {
         cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM);
         attr = true;
     }
-    const int nblk = chol_nblk(a.N);
+    const int N = a.N;
+    const int nblk = chol_nblk(N);
     const long stride_dinv = (long)nblk * NB * NB;
-    // Look-ahead: the latency-bound chain  diag(k) -> panel(k)  runs on the aux stream and overlaps the
-    // FP64-bound trailing update of step k-1; the main stream only hands over the next block column early.
-    const bool la = a.aux != nullptr && a.ev != nullptr && nblk > 2;
-    cudaStream_t sp = la ? a.aux : s;  // stream of the panel chain
+    constexpr int OB = 2 * NB;  // outer block: the trailing update is a rank-256 GEMM (two 128-wide panels)
+    // Look-ahead: the latency-bound chain  diag -> panel -> inner update -> diag -> panel  runs on the aux stream and
+    // overlaps the FP64-bound trailing update of the previous outer step; the main stream hands over the next
+    // 256 columns early.
+    const bool la = a.aux != nullptr && a.ev != nullptr && N > 2 * OB;
+    cudaStream_t sp = la ? a.aux : s;
     if (la) {
         cudaEventRecord(a.ev[0], s);
         cudaStreamWaitEvent(sp, a.ev[0], 0);
     }
-    for (int kb = 0; kb < nblk; ++kb) {
-        const int k0 = kb * NB;
-        const int nb = a.N - k0 < NB ? a.N - k0 : NB;
-        cudaEvent_t ev_col = la ? a.ev[2 * (kb & 1)] : nullptr, ev_panel = la ? a.ev[2 * (kb & 1) + 1] : nullptr;
+    auto diag = [&](int k0, int nb) {
         DiagArgs d;
         d.A = a.A + (long)k0 * a.lda + k0;
         d.lda = a.lda;
         d.strideA = a.strideA;
         d.nb = nb;
         d.k0 = k0;
-        d.dinv = a.dinv + (long)kb * NB * NB;
+        d.dinv = a.dinv + (long)(k0 / NB) * NB * NB;
         d.stride_dinv = stride_dinv;
         d.logd = a.logd + k0;
-        d.stride_logd = a.N;
+        d.stride_logd = N;
         d.d_info = a.d_info;
         d.info_vec = a.info_vec;
-        if (la && kb > 0) cudaStreamWaitEvent(sp, ev_col, 0);  // block column kb fully updated
         potrf_diag_kernel<<<a.batch, DIAG_THREADS, DIAG_SMEM, sp>>>(d);
-        const int rem = a.N - k0 - nb;
-        if (rem <= 0) break;
-        double* panel = a.A + (long)(k0 + nb) * a.lda + k0;
-        // panel <- panel * inv(L11)^T   (in place: one 128-wide column tile, so every CTA only
-        // rewrites the rows it alone reads)
+    };
+    // rows [r0, N) of block column [k0, k0+nb)  <-  (same) * inv(L_kk)^T     (in place, one 128-wide column tile)
+    auto panel = [&](int k0, int nb, int r0) -> int {
+        if (N - r0 <= 0) return 0;
+        double* P = a.A + (long)r0 * a.lda + k0;
         GemmArgs g;
         g.transA = false; g.transB = true;
-        g.M = rem; g.N = nb; g.K = nb;
-        g.alpha = 1.0; g.beta = 0.0;
-        g.A = panel; g.lda = a.lda; g.strideA = a.strideA;
-        g.B = d.dinv; g.ldb = NB; g.strideB = stride_dinv;
-        g.C = panel; g.ldc = a.lda; g.strideC = a.strideA;
+        g.M = N - r0; g.N = nb; g.K = nb;
+        g.A = P; g.lda = a.lda; g.strideA = a.strideA;
+        g.B = a.dinv + (long)(k0 / NB) * NB * NB; g.ldb = NB; g.strideB = stride_dinv;
+        g.C = P; g.ldc = a.lda; g.strideC = a.strideA;
         g.batch = a.batch;
         g.small_tiles = 0;
-        if (launch_gemm(sp, g)) return -2;
+        return launch_gemm(sp, g);
+    };
+    // C[rows r0.., cols c0..c0+nc) -= P[rows r0.., k0..k0+kw) * P[rows c0..c0+nc, k0..k0+kw)^T
+    auto update = [&](cudaStream_t st, int r0, int c0, int nc, int k0, int kw, int lower) -> int {
+        if (N - r0 <= 0 || nc <= 0) return 0;
+        GemmArgs t;
+        t.transA = false; t.transB = true;
+        t.M = N - r0; t.N = nc; t.K = kw;
+        t.alpha = -1.0; t.beta = 1.0;
+        t.A = a.A + (long)r0 * a.lda + k0; t.lda = a.lda; t.strideA = a.strideA;
+        t.B = a.A + (long)c0 * a.lda + k0; t.ldb = a.lda; t.strideB = a.strideA;
+        t.C = a.A + (long)r0 * a.lda + c0; t.ldc = a.lda; t.strideC = a.strideA;
+        t.batch = a.batch;
+        t.lower_only = lower;
+        return launch_gemm(st, t);
+    };
+    int step = 0;
+    for (int K0 = 0; K0 < N; K0 += OB, ++step) {
+        const int w = N - K0 < OB ? N - K0 : OB;
+        const int nb1 = w < NB ? w : NB, nb2 = w - nb1;
+        cudaEvent_t ev_col = la ? a.ev[2 * (step & 1)] : nullptr, ev_panel = la ? a.ev[2 * (step & 1) + 1] : nullptr;
+        if (la && step > 0) cudaStreamWaitEvent(sp, ev_col, 0);  // columns [K0, K0+w) fully updated
+        diag(K0, nb1);
+        if (panel(K0, nb1, K0 + nb1)) return -2;
+        if (nb2 > 0) {
+            if (update(sp, K0 + nb1, K0 + nb1, nb2, K0, nb1, 0)) return -2;  // second half of the outer block
+            diag(K0 + nb1, nb2);
+            if (panel(K0 + nb1, nb2, K0 + w)) return -2;
+        }
+        const int rem = N - K0 - w;
+        if (rem <= 0) break;
         if (la) {
             cudaEventRecord(ev_panel, sp);
             cudaStreamWaitEvent(s, ev_panel, 0);
         }
-        // trailing <- trailing - panel panel^T  (lower tiles); with look-ahead the next block column first
-        const int ncol = la ? (rem < NB ? rem : NB) : 0;
+        // trailing <- trailing - P P^T with P = A[K0+w:, K0:K0+w]  (rank-w update, lower tiles)
+        const int ncol = la ? (rem < OB ? rem : OB) : 0;
         if (la) {
-            GemmArgs c;
-            c.transA = false; c.transB = true;
-            c.M = rem; c.N = ncol; c.K = nb;
-            c.alpha = -1.0; c.beta = 1.0;
-            c.A = panel; c.lda = a.lda; c.strideA = a.strideA;
-            c.B = panel; c.ldb = a.lda; c.strideB = a.strideA;
-            c.C = a.A + (long)(k0 + nb) * a.lda + (k0 + nb); c.ldc = a.lda; c.strideC = a.strideA;
-            c.batch = a.batch;
-            c.small_tiles = 0;
-            if (launch_gemm(s, c)) return -2;
-            cudaEventRecord(a.ev[2 * ((kb + 1) & 1)], s);  // ev_col of step kb + 1
+            if (update(s, K0 + w, K0 + w, ncol, K0, w, 1)) return -2;  // next outer block column first (lower tiles)
+            cudaEventRecord(a.ev[2 * ((step + 1) & 1)], s);
         }
-        const int rest = rem - ncol;
-        if (rest > 0) {
-            double* p2 = panel + (long)ncol * a.lda;
-            GemmArgs t;
-            t.transA = false; t.transB = true;
-            t.M = rest; t.N = rest; t.K = nb;
-            t.alpha = -1.0; t.beta = 1.0;
-            t.A = p2; t.lda = a.lda; t.strideA = a.strideA;
-            t.B = p2; t.ldb = a.lda; t.strideB = a.strideA;
-            t.C = a.A + (long)(k0 + nb + ncol) * a.lda + (k0 + nb + ncol); t.ldc = a.lda; t.strideC = a.strideA;
-            t.batch = a.batch;
-            t.lower_only = 1;
-            if (launch_gemm(s, t)) return -2;
-        }
+        if (rem - ncol > 0 && update(s, K0 + w + ncol, K0 + w + ncol, rem - ncol, K0, w, 1)) return -2;
     }
     if (la) {  // the main stream owns the result again
         cudaEventRecord(a.ev[0], sp);
