@@ -1,0 +1,34 @@
+"""torchrun script: time the distributed exact-GP NLML (1-D block-cyclic Cholesky over NCCL)."""
+import json, os, sys, time
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from multi_fidelity_gpflow_b200 import _lib
+from multi_fidelity_gpflow_b200.dist_chol import distributed_gpr_nlml
+from oracle import mfgp_oracle as onp
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+h = _lib.Handle(rank)
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+nbd = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+ds = onp.synthetic_exact_dataset(N)
+res = {}
+for rep in range(3):
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    v = distributed_gpr_nlml(h, ds["X"], ds["Y"], ds["theta"], ds["noise"], nbd=nbd)
+    torch.cuda.synchronize(); dist.barrier()
+    dt = time.perf_counter() - t0
+    if rank == 0:
+        print(f"world={world} N={N} nbd={nbd} rep {rep}: {dt*1e3:.1f} ms  {N**3/3/dt/1e12:.2f} TFLOP/s (potrf flops)  nlml={v:.6f}", flush=True)
+        res = {"world": world, "N": N, "nbd": nbd, "sec": dt, "potrf_tflops": N**3 / 3 / dt / 1e12, "nlml": v}
+if rank == 0:
+    h.set_stream(None)
+    if N <= 16384:
+        t0 = time.perf_counter(); single = h.gpr_nlml(ds["X"], ds["Y"], ds["theta"], ds["noise"]); dt1 = time.perf_counter() - t0
+        res["single_gpu_nlml"] = single; res["single_gpu_sec"] = dt1
+        print("single-GPU nlml", single, f"{dt1*1e3:.1f} ms", "rel diff", abs(single - res["nlml"]) / abs(single))
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(res, open(f"gpurun_out/dist_chol_w{world}_N{N}.json", "w"))
+dist.destroy_process_group()
