@@ -202,8 +202,8 @@ int mfgp_gpr_batched_nlml_grad(mfgp_handle* h, const double* X, int N, int d, co
         SmallArgs a{};
         a.X = dX; a.N = N; a.d = d; a.Y = dY; a.ldy = ldy; a.ycols = ycols; a.B = B;
         a.theta = dth; a.noise = dnz; a.nlml = dn; a.grad = dg; a.info = di; a.d_info = h->d_info;
-        static const bool use_v1 = [] { const char* e = getenv("MFGP_SMALL_KERNEL"); return e && e[0] == '1'; }();
-        if ((use_v1 ? launch_gpr_small(h->stream, a) : launch_gpr_small_mma(h->stream, a)))
+        static const int which = [] { const char* e = getenv("MFGP_SMALL_KERNEL"); return e ? atoi(e) : 4; }();
+        if ((which == 1 ? launch_gpr_small(h->stream, a) : which == 2 ? launch_gpr_small_mma(h->stream, a) : launch_gpr_small_v4(h->stream, a)))
             return mfgp_fail(h, MFGP_ERR_CUDA, "gpr_small launch failed");
     } else {
         // blocked path, chunked so that 3 N^2 workspaces per problem fit comfortably

@@ -22,3 +22,4 @@ struct SmallArgs {
 };
 int launch_gpr_small(cudaStream_t s, const SmallArgs& a);      // v1: one CTA per problem (DFMA)
 int launch_gpr_small_mma(cudaStream_t s, const SmallArgs& a);  // v2: one warp per problem (DMMA tiles)
+int launch_gpr_small_v4(cudaStream_t s, const SmallArgs& a);   // v4: persistent, compact code, 12 warps per SM

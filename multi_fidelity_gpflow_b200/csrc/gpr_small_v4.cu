@@ -1,0 +1,629 @@
+// gpr_small_v4.cu -- K6 v4: batched small-matrix NLML + analytic gradient, one warp per problem,
+// PERSISTENT grid, compact instruction stream, 12 problems in flight per SM.
+//
+// What changed against v2/v3 (gpr_small_mma.cu), and why (profiles/r01_ncu_gpr_small_final.csv):
+//   * v3's fully unrolled body is ~300 KB of SASS; with 8 warps at 8 different program counters the dominant
+//     stall was `no_instruction` (2.0 cycles per issued instruction) and the 234 registers capped the SM at 8 warps.
+//     Here the covariance assembly / dK recompute (the exp-heavy part) and the 8x8 diagonal-tile factorisation are
+//     single-copy runtime loops; only the DMMA tile products are unrolled (a few KB).  The kernel fits the 32 KB
+//     L1.5 instruction cache, needs no __syncthreads re-alignment, and runs at <= 168 registers = 12 warps per SM.
+//   * K^-1 = W^T W is formed IN PLACE row block by row block (LAPACK lauum order), so its accumulators are one block
+//     row (14 doubles) instead of the whole triangle (56 doubles).
+//   * a = W y and alpha = W^T a are DFMA dot products + 4-lane shuffles instead of one-column DMMA products
+//     (a one-column DMMA wastes 7/8 of the FP64 pipe time it occupies).
+//   * tiles are packed by COLUMN: tile(i, j) = column base(j) + (i - j), so the left-looking update addresses
+//     tile(kb + u, k) as pointer + constant.
+//   * the discrepancy kernel (HF x HF pairs only) is evaluated pair-wise from the raw inputs; no per-warp copy of
+//     delta-scaled coordinates; the row scale s_i and -|x_i|^2/2 + log(var_L)/2 are one interleaved array.
+//
+// Algorithm (per problem; N <= 64 padded to NT tiles of 8):
+//   1  K = fused MF covariance (+ noise; identity on padding rows) -> lower tiles in shared memory
+//   2  left-looking tile Cholesky; diagonal slot keeps inv(L_kk); panel = A_ik inv(L_kk)^T (DMMA)
+//   3  W = L^-1 row block by row block: W_ij = -W_ii sum_k L_ik W_kj (DMMA)
+//   4  a = W y, alpha = W^T a;  nlml = |a|^2/2 + sum log L_ii + N/2 log 2 pi
+//   5  K^-1 in place, G = alpha alpha^T - K^-1 (weighted by multiplicity)
+//   6  gradient: sum G o dK/dtheta with K^L recomputed tile by tile
+// Replaces, per bin, GPR.log_marginal_likelihood + tape.gradient (reference mfgpflow/linear.py:206-207).
+#include <cmath>
+#include <cstdint>
+
+#include "gpr_small.cuh"
+#include "mathx.cuh"
+
+namespace {
+
+constexpr int WPC = 4;  // warps (= problems in flight) per CTA
+constexpr double LOG2PI = 1.8378770664093454835606594728112;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double quad_sum(double v) {  // sum over the 4 lanes that share g
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+// element offset (doubles) inside a 64-double tile: 16-byte chunks of a row XOR-swizzled by (row & 2)
+__host__ __device__ __forceinline__ constexpr int tile_off(int r, int c) {
+    return r * 8 + ((((c >> 1) ^ (r & 2))) << 1) + (c & 1);
+}
+template <int NT>
+__host__ __device__ __forceinline__ constexpr int cslot(int i, int j) {  // i >= j, packed by column
+    return j * NT - j * (j - 1) / 2 + (i - j);
+}
+
+template <int NT>
+__device__ __forceinline__ int cslot_rt(int i, int j) {
+    return j * NT - j * (j - 1) / 2 + (i - j);
+}
+
+template <int NT>
+struct WarpMem {
+    static constexpr int NP = 8 * NT;
+    static constexpr int NTRI = NT * (NT + 1) / 2;
+    double* tiles;  // [NTRI][64]
+    double* xL;     // [d][NP]   inputs / ls_L
+    double* hs;     // [NP][2]   { -|xL|^2/2 + log(var_L)/2 , row scale s in {0, 1, rho} }
+    double* yv;     // [NP]      y, later alpha
+    double* av;     // [NP]      a = W y
+    double* inv;    // [2d]      1/ls_L, 1/ls_delta
+    double* red;    // [2d+4]
+    unsigned char* hidx;  // [NP] indices of the HF rows
+    __host__ __device__ static size_t doubles(int d) {
+        return (size_t)NTRI * 64 + (size_t)d * NP + 4 * NP + 2 * d + (2 * d + 4) + NP / 8 + 2;
+    }
+    __device__ WarpMem(double* base, int d) {
+        tiles = base;
+        xL = tiles + NTRI * 64;
+        hs = xL + d * NP;
+        yv = hs + 2 * NP;
+        av = yv + NP;
+        inv = av + NP;
+        red = inv + 2 * d;
+        hidx = reinterpret_cast<unsigned char*>(red + 2 * d + 4);
+    }
+};
+
+// K^L C-fragment of tile (i, j): rows 8i+g, columns 8j+2t, 8j+2t+1.  Expanded-square distance folded into the
+// exponent; log(var_L) is split over the two row terms.  With DS > 0 the scaled coordinates are returned for reuse.
+template <int NT, int DS>
+__device__ __forceinline__ void kl_tile(const WarpMem<NT>& m, int d, int i, int j, int g, int t, double& k0, double& k1,
+                                        double* xr, double* xc0, double* xc1) {
+    constexpr int NP = 8 * NT;
+    const int r = 8 * i + g, c = 8 * j + 2 * t;
+    double e0 = 0.0, e1 = 0.0;
+    if constexpr (DS > 0) {
+#pragma unroll
+        for (int q = 0; q < DS; ++q) {
+            const double a = m.xL[q * NP + r];
+            const double2 b = *reinterpret_cast<const double2*>(m.xL + q * NP + c);
+            xr[q] = a;
+            xc0[q] = b.x;
+            xc1[q] = b.y;
+            e0 = fma(a, b.x, e0);
+            e1 = fma(a, b.y, e1);
+        }
+    } else {
+        for (int q = 0; q < d; ++q) {
+            const double a = m.xL[q * NP + r];
+            const double2 b = *reinterpret_cast<const double2*>(m.xL + q * NP + c);
+            e0 = fma(a, b.x, e0);
+            e1 = fma(a, b.y, e1);
+        }
+    }
+    const double2 hr = *reinterpret_cast<const double2*>(m.hs + 2 * r);
+    const double2 h0 = *reinterpret_cast<const double2*>(m.hs + 2 * c);
+    const double2 h1 = *reinterpret_cast<const double2*>(m.hs + 2 * c + 2);
+    k0 = (hr.y * h0.y) * fexp(e0 + (hr.x + h0.x));
+    k1 = (hr.y * h1.y) * fexp(e1 + (hr.x + h1.x));
+}
+
+template <int NT>
+__device__ __forceinline__ void next_tile(int& i, int& j) {  // column-packed order
+    if (++i == NT) {
+        ++j;
+        i = j;
+    }
+}
+
+template <int NT, int DS>
+__global__ void __launch_bounds__(WPC * 32, 3) gpr_small_v4_kernel(SmallArgs p, int warp_doubles) {
+    constexpr int NP = 8 * NT;
+    constexpr int NTRI = NT * (NT + 1) / 2;
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int N = p.N, d = (DS > 0) ? DS : p.d;
+    const WarpMem<NT> m(smem + (size_t)warp * warp_doubles, d);
+    const int g = lane >> 2, t = lane & 3;
+    const int cst = tile_off(g, 2 * t);                                // C fragment: row g, cols 2t, 2t+1
+    const int km0 = tile_off(g, t), km1 = tile_off(g, t + 4);          // K-major fragment: (row g, col t + 4s)
+    const int mm0 = tile_off(t, g), mm1 = tile_off(t + 4, g);          // M-major fragment: (row t + 4s, col g)
+    const int nq = 2 * d + 4;
+
+    for (int prob = blockIdx.x * WPC + warp; prob < p.B; prob += gridDim.x * WPC) {
+        // ---- setup --------------------------------------------------------------------------------
+        const double* __restrict__ theta = p.theta + (size_t)prob * (2 * d + 3);
+        if (lane < 2 * d) m.inv[lane] = 1.0 / theta[lane < d ? 1 + lane : 2 + lane];
+        const double rho = theta[0], vL = theta[1 + d], vD = theta[2 + 2 * d];
+        const double noise = p.noise[prob];
+        const double hlv = 0.5 * log(vL);
+        __syncwarp();
+        int nH = 0;
+        unsigned long long hfmask = 0ull;  // bit r: row r is a high-fidelity point
+#pragma unroll
+        for (int pass = 0; pass < (NP + 31) / 32; ++pass) {
+            const int r = lane + 32 * pass;
+            bool live = false, hf = false;
+            if (r < N) {
+                const double fid = p.X[(size_t)r * (d + 1) + d];
+                hf = (fid == 1.0);
+                live = hf || (fid == 0.0);
+            }
+            if (r < NP) {
+                double nL = 0.0;
+                for (int q = 0; q < d; ++q) {
+                    const double x = live ? p.X[(size_t)r * (d + 1) + q] * m.inv[q] : 0.0;
+                    m.xL[q * NP + r] = x;
+                    nL = fma(x, x, nL);
+                }
+                *reinterpret_cast<double2*>(m.hs + 2 * r) = make_double2(fma(-0.5, nL, hlv), live ? (hf ? rho : 1.0) : 0.0);
+                m.yv[r] = (r < N) ? p.Y[(size_t)r * p.ldy + prob % p.ycols] : 0.0;
+            }
+            const unsigned hm = __ballot_sync(0xffffffffu, hf);
+            if (hf) m.hidx[nH + __popc(hm & ((1u << lane) - 1u))] = (unsigned char)r;
+            nH += __popc(hm);
+            hfmask |= (unsigned long long)hm << (32 * pass);
+        }
+        __syncwarp();
+
+        // ---- 1: covariance tiles --------------------------------------------------------------------
+        {
+            int i = 0, j = 0;
+#pragma unroll 1
+            for (int s = 0; s < NTRI; s += 2) {
+                const int ia = i, ja = j;
+                next_tile<NT>(i, j);
+                const bool two = (s + 1 < NTRI);
+                const int ib = two ? i : ia, jb = two ? j : ja;
+                next_tile<NT>(i, j);
+                double ka0, ka1, kb0, kb1;
+                kl_tile<NT, 0>(m, d, ia, ja, g, t, ka0, ka1, nullptr, nullptr, nullptr);
+                kl_tile<NT, 0>(m, d, ib, jb, g, t, kb0, kb1, nullptr, nullptr, nullptr);
+                if (ia == ja) {  // diagonal: + noise (real rows) or identity (padding rows keep the factorisation well posed)
+                    const double dg = (8 * ia + g < N) ? noise : 1.0;
+                    if (g == 2 * t) ka0 += dg;
+                    if (g == 2 * t + 1) ka1 += dg;
+                }
+                if (ib == jb) {
+                    const double dg = (8 * ib + g < N) ? noise : 1.0;
+                    if (g == 2 * t) kb0 += dg;
+                    if (g == 2 * t + 1) kb1 += dg;
+                }
+                *reinterpret_cast<double2*>(m.tiles + s * 64 + cst) = make_double2(ka0, ka1);
+                if (two) *reinterpret_cast<double2*>(m.tiles + (s + 1) * 64 + cst) = make_double2(kb0, kb1);
+            }
+        }
+        __syncwarp();
+        // discrepancy GP on HF x HF pairs (lower triangle incl. diagonal), straight from the raw inputs
+        const int npairs = nH * (nH + 1) / 2;
+        for (int tt = lane; tt < npairs; tt += 32) {
+            int pi = (int)((sqrt(8.0 * tt + 1.0) - 1.0) * 0.5);
+            while ((pi + 1) * (pi + 2) / 2 <= tt) ++pi;
+            while (pi * (pi + 1) / 2 > tt) --pi;
+            const int pj = tt - pi * (pi + 1) / 2;
+            const int ri = m.hidx[pi], rj = m.hidx[pj];  // ri >= rj
+            double ee = 0.0;
+            for (int q = 0; q < d; ++q) {
+                const double df = (p.X[(size_t)ri * (d + 1) + q] - p.X[(size_t)rj * (d + 1) + q]) * m.inv[d + q];
+                ee = fma(df, df, ee);
+            }
+            m.tiles[cslot_rt<NT>(ri >> 3, rj >> 3) * 64 + tile_off(ri & 7, rj & 7)] += vD * fexp(-0.5 * ee);
+        }
+        __syncwarp();
+
+        // ---- 2: left-looking tile Cholesky ------------------------------------------------------------
+        int bad = 0;
+        double logdet2 = 0.0;
+        {
+#pragma unroll 1
+            for (int kb = 0; kb < NT; ++kb) {
+                const int cnt = NT - kb;
+                double acc[NT][2];
+#pragma unroll
+                for (int u = 0; u < NT; ++u) acc[u][0] = acc[u][1] = 0.0;
+                double* pk = m.tiles + kb * 64;  // tile(kb, 0); tile(kb + u, k) = pk + u * 64
+#pragma unroll 1
+                for (int k = 0; k < kb; ++k) {
+                    const double b0 = pk[km0], b1 = pk[km1];
+                    dmma(acc[0][0], acc[0][1], b0, b0);
+                    dmma(acc[0][0], acc[0][1], b1, b1);
+#pragma unroll
+                    for (int u = 1; u < NT; ++u)
+                        if (u < cnt) {
+                            const double a0 = pk[u * 64 + km0], a1 = pk[u * 64 + km1];
+                            dmma(acc[u][0], acc[u][1], a0, b0);
+                            dmma(acc[u][0], acc[u][1], a1, b1);
+                        }
+                    pk += (NT - k - 1) * 64;
+                }
+                // pk == tile(kb, kb).  acc = K - sum
+#pragma unroll
+                for (int u = 0; u < NT; ++u)
+                    if (u < cnt) {
+                        const double2 c = *reinterpret_cast<const double2*>(pk + u * 64 + cst);
+                        acc[u][0] = c.x - acc[u][0];
+                        acc[u][1] = c.y - acc[u][1];
+                    }
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < NT; ++u)
+                    if (u < cnt) *reinterpret_cast<double2*>(pk + u * 64 + cst) = make_double2(acc[u][0], acc[u][1]);
+                __syncwarp();
+                // K-major fragments of the raw panel tiles (re-using acc as storage), before they are overwritten
+#pragma unroll
+                for (int u = 1; u < NT; ++u)
+                    if (u < cnt) {
+                        acc[u][0] = pk[u * 64 + km0];
+                        acc[u][1] = pk[u * 64 + km1];
+                    }
+                // diagonal tile: every lane factors the 8x8 block in registers (no shuffles), lanes 0-7 invert it
+                {
+                    double a[8][8], rinv[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+#pragma unroll
+                        for (int c2 = 0; c2 <= r / 2; ++c2) {
+                            const double2 v = *reinterpret_cast<const double2*>(pk + r * 8 + ((c2 ^ (r & 2)) << 1));
+                            a[r][2 * c2] = v.x;
+                            a[r][2 * c2 + 1] = v.y;
+                        }
+                    double prod = 1.0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        double piv = a[j][j];
+                        if (!(piv > 0.0)) {
+                            if (!bad) bad = 8 * kb + j + 1;
+                            piv = nan("");
+                        }
+                        prod *= piv;
+                        const double ri = rsqrt(piv);
+                        rinv[j] = ri;
+#pragma unroll
+                        for (int i = j + 1; i < 8; ++i) a[i][j] *= ri;
+#pragma unroll
+                        for (int k = j + 1; k < 8; ++k)
+#pragma unroll
+                            for (int i = k; i < 8; ++i) a[i][k] = fma(-a[i][j], a[k][j], a[i][k]);
+                    }
+                    logdet2 += log(prod);
+                    const int c = lane & 7;  // column c of inv(L_kk) by forward substitution
+                    double w[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        double s = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+                        for (int k = 0; k < i; ++k) s = fma(-a[i][k], w[k], s);
+                        w[i] = s * rinv[i];
+                    }
+                    __syncwarp();  // every lane has read the raw diagonal tile
+                    if (lane < 8) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) pk[tile_off(i, c)] = w[i];
+                    }
+                }
+                __syncwarp();
+                // panel: L_ik = A_ik inv(L_kk)^T
+                {
+                    const double wb0 = pk[km0], wb1 = pk[km1];
+#pragma unroll
+                    for (int u = 1; u < NT; ++u)
+                        if (u < cnt) {
+                            double c0 = 0.0, c1 = 0.0;
+                            dmma(c0, c1, acc[u][0], wb0);
+                            dmma(c0, c1, acc[u][1], wb1);
+                            *reinterpret_cast<double2*>(pk + u * 64 + cst) = make_double2(c0, c1);
+                        }
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---- 3: W = L^-1, row block by row block -------------------------------------------------------
+#pragma unroll
+        for (int i = 1; i < NT; ++i) {
+            double la[NT][2], acc[NT][2];
+#pragma unroll
+            for (int k = 0; k < i; ++k) {
+                la[k][0] = m.tiles[cslot<NT>(i, k) * 64 + km0];
+                la[k][1] = m.tiles[cslot<NT>(i, k) * 64 + km1];
+            }
+#pragma unroll
+            for (int j = 0; j < i; ++j) {
+                acc[j][0] = acc[j][1] = 0.0;
+#pragma unroll
+                for (int k = j; k < i; ++k) {
+                    dmma(acc[j][0], acc[j][1], la[k][0], m.tiles[cslot<NT>(k, j) * 64 + mm0]);
+                    dmma(acc[j][0], acc[j][1], la[k][1], m.tiles[cslot<NT>(k, j) * 64 + mm1]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < i; ++j)
+                *reinterpret_cast<double2*>(m.tiles + cslot<NT>(i, j) * 64 + cst) = make_double2(acc[j][0], acc[j][1]);
+            __syncwarp();
+            const double w0 = -m.tiles[cslot<NT>(i, i) * 64 + km0], w1 = -m.tiles[cslot<NT>(i, i) * 64 + km1];
+#pragma unroll
+            for (int j = 0; j < i; ++j) {
+                acc[j][0] = acc[j][1] = 0.0;
+                dmma(acc[j][0], acc[j][1], w0, m.tiles[cslot<NT>(i, j) * 64 + mm0]);
+                dmma(acc[j][0], acc[j][1], w1, m.tiles[cslot<NT>(i, j) * 64 + mm1]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < i; ++j)
+                *reinterpret_cast<double2*>(m.tiles + cslot<NT>(i, j) * 64 + cst) = make_double2(acc[j][0], acc[j][1]);
+            __syncwarp();
+        }
+
+        // ---- 4: a = W y, alpha = W^T a, value ------------------------------------------------------------
+        double quad = 0.0;
+        {
+            double2 yy[NT];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) yy[j] = *reinterpret_cast<const double2*>(m.yv + 8 * j + 2 * t);
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                double s = 0.0;
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    const double2 w = *reinterpret_cast<const double2*>(m.tiles + cslot<NT>(i, j) * 64 + cst);
+                    s = fma(w.x, yy[j].x, s);
+                    s = fma(w.y, yy[j].y, s);
+                }
+                s = quad_sum(s);
+                if (t == 0) {
+                    m.av[8 * i + g] = s;
+                    quad = fma(s, s, quad);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                double s = 0.0;
+#pragma unroll
+                for (int i = j; i < NT; ++i) {
+                    s = fma(m.tiles[cslot<NT>(i, j) * 64 + mm0], m.av[8 * i + t], s);
+                    s = fma(m.tiles[cslot<NT>(i, j) * 64 + mm1], m.av[8 * i + t + 4], s);
+                }
+                s = quad_sum(s);
+                if (t == 0) m.yv[8 * j + g] = s;  // alpha overwrites y
+            }
+            quad = warp_sum(quad);
+            if (lane == 0) {
+                p.nlml[prob] = 0.5 * quad + 0.5 * logdet2 + 0.5 * N * LOG2PI;
+                if (p.info) p.info[prob] = bad;
+                if (bad) atomicCAS(p.d_info, 0, bad);
+            }
+        }
+        if (!p.grad) {
+            __syncwarp();
+            continue;
+        }
+        __syncwarp();
+
+        // ---- 5: K^-1 = W^T W in place (row blocks ascending), G = w o (alpha alpha^T - K^-1) -----------------
+        double s_dg = 0.0;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            double acc[NT][2];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) acc[j][0] = acc[j][1] = 0.0;
+#pragma unroll
+            for (int k = i; k < NT; ++k) {
+                const double a0 = m.tiles[cslot<NT>(k, i) * 64 + mm0], a1 = m.tiles[cslot<NT>(k, i) * 64 + mm1];
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    const double b0 = (j == i) ? a0 : m.tiles[cslot<NT>(k, j) * 64 + mm0];
+                    const double b1 = (j == i) ? a1 : m.tiles[cslot<NT>(k, j) * 64 + mm1];
+                    dmma(acc[j][0], acc[j][1], a0, b0);
+                    dmma(acc[j][0], acc[j][1], a1, b1);
+                }
+            }
+            __syncwarp();  // row block i of W is dead from here on
+            const int r = 8 * i + g;
+            const double alr = m.yv[r];
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                const int c0 = 8 * j + 2 * t;
+                const double2 alc = *reinterpret_cast<const double2*>(m.yv + c0);
+                double g0 = fma(alr, alc.x, -acc[j][0]), g1 = fma(alr, alc.y, -acc[j][1]);
+                // multiplicity: strictly lower counted twice, diagonal once; upper part of diagonal tiles and padding zero
+                double w0 = (c0 < r) ? 2.0 : (c0 == r ? 1.0 : 0.0), w1 = (c0 + 1 < r) ? 2.0 : (c0 + 1 == r ? 1.0 : 0.0);
+                if (r >= N) w0 = w1 = 0.0;
+                g0 *= w0;
+                g1 *= w1;
+                if (j == i) {
+                    if (c0 == r) s_dg += g0;
+                    if (c0 + 1 == r) s_dg += g1;
+                }
+                *reinterpret_cast<double2*>(m.tiles + cslot<NT>(i, j) * 64 + cst) = make_double2(g0, g1);
+            }
+        }
+        __syncwarp();
+
+        // ---- 6: gradient contraction --------------------------------------------------------------------
+        // discrepancy kernel first (needs G at the HF x HF pairs, before T^L overwrites anything)
+        for (int q = lane; q < nq; q += 32) m.red[q] = 0.0;
+        __syncwarp();
+        for (int t0 = 0; t0 < npairs; t0 += 32) {
+            const int tt = t0 + lane;
+            double td = 0.0;
+            int ri = 0, rj = 0;
+            if (tt < npairs) {
+                int pi = (int)((sqrt(8.0 * tt + 1.0) - 1.0) * 0.5);
+                while ((pi + 1) * (pi + 2) / 2 <= tt) ++pi;
+                while (pi * (pi + 1) / 2 > tt) --pi;
+                const int pj = tt - pi * (pi + 1) / 2;
+                ri = m.hidx[pi];
+                rj = m.hidx[pj];
+                double ee = 0.0;
+                for (int q = 0; q < d; ++q) {
+                    const double df = (p.X[(size_t)ri * (d + 1) + q] - p.X[(size_t)rj * (d + 1) + q]) * m.inv[d + q];
+                    ee = fma(df, df, ee);
+                }
+                td = m.tiles[cslot_rt<NT>(ri >> 3, rj >> 3) * 64 + tile_off(ri & 7, rj & 7)] * vD * fexp(-0.5 * ee);
+            }
+            const double sv = warp_sum(td);
+            if (lane == 0) m.red[2 + 2 * d] += sv;
+            for (int q = 0; q < d; ++q) {
+                const double df = (p.X[(size_t)ri * (d + 1) + q] - p.X[(size_t)rj * (d + 1) + q]) * m.inv[d + q];
+                const double sq = warp_sum(td * df * df);
+                if (lane == 0) m.red[2 + d + q] += sq;
+            }
+        }
+        double s_vL = 0.0, s_rho = 0.0;
+        if constexpr (DS > 0) {
+            double sL[DS];
+#pragma unroll
+            for (int q = 0; q < DS; ++q) sL[q] = 0.0;
+            int i = 0, j = 0;
+#pragma unroll 1
+            for (int s = 0; s < NTRI; s += 2) {
+                const int ia = i, ja = j;
+                next_tile<NT>(i, j);
+                const bool two = (s + 1 < NTRI);
+                const int ib = two ? i : ia, jb = two ? j : ja;
+                next_tile<NT>(i, j);
+                double ka0, ka1, kb0, kb1;
+                double xra[DS], xa0[DS], xa1[DS], xrb[DS], xb0[DS], xb1[DS];
+                kl_tile<NT, DS>(m, d, ia, ja, g, t, ka0, ka1, xra, xa0, xa1);
+                kl_tile<NT, DS>(m, d, ib, jb, g, t, kb0, kb1, xrb, xb0, xb1);
+                const double2 ga = *reinterpret_cast<const double2*>(m.tiles + s * 64 + cst);
+                double2 gb = *reinterpret_cast<const double2*>(m.tiles + (two ? s + 1 : s) * 64 + cst);
+                if (!two) gb.x = gb.y = 0.0;
+                const double ta0 = ga.x * ka0, ta1 = ga.y * ka1, tb0 = gb.x * kb0, tb1 = gb.y * kb1;
+                // exponent of rho in s_i s_j: number of HF points in the pair (s == rho exactly on HF rows)
+                const double hra = (double)((hfmask >> (8 * ia + g)) & 1ull), hrb = (double)((hfmask >> (8 * ib + g)) & 1ull);
+                const double hca0 = (double)((hfmask >> (8 * ja + 2 * t)) & 1ull), hca1 = (double)((hfmask >> (8 * ja + 2 * t + 1)) & 1ull);
+                const double hcb0 = (double)((hfmask >> (8 * jb + 2 * t)) & 1ull), hcb1 = (double)((hfmask >> (8 * jb + 2 * t + 1)) & 1ull);
+                s_vL += (ta0 + ta1) + (tb0 + tb1);
+                s_rho += ta0 * (hra + hca0) + ta1 * (hra + hca1) + tb0 * (hrb + hcb0) + tb1 * (hrb + hcb1);
+#pragma unroll
+                for (int q = 0; q < DS; ++q) {
+                    const double da0 = xra[q] - xa0[q], da1 = xra[q] - xa1[q], db0 = xrb[q] - xb0[q], db1 = xrb[q] - xb1[q];
+                    sL[q] = fma(ta0 * da0, da0, sL[q]);
+                    sL[q] = fma(ta1 * da1, da1, sL[q]);
+                    sL[q] = fma(tb0 * db0, db0, sL[q]);
+                    sL[q] = fma(tb1 * db1, db1, sL[q]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < DS; ++q) {
+                const double v = warp_sum(sL[q]);
+                if (lane == 0) m.red[1 + q] = v;
+            }
+        } else {
+            // generic d: T^L = G o K^L overwrites G, then one pass per dimension
+            int i = 0, j = 0;
+#pragma unroll 1
+            for (int s = 0; s < NTRI; ++s) {
+                double k0, k1;
+                kl_tile<NT, 0>(m, d, i, j, g, t, k0, k1, nullptr, nullptr, nullptr);
+                const double2 gg = *reinterpret_cast<const double2*>(m.tiles + s * 64 + cst);
+                const double t0 = gg.x * k0, t1 = gg.y * k1;
+                const double hr = (double)((hfmask >> (8 * i + g)) & 1ull);
+                const double hc0 = (double)((hfmask >> (8 * j + 2 * t)) & 1ull), hc1 = (double)((hfmask >> (8 * j + 2 * t + 1)) & 1ull);
+                s_vL += t0 + t1;
+                s_rho += t0 * (hr + hc0) + t1 * (hr + hc1);
+                *reinterpret_cast<double2*>(m.tiles + s * 64 + cst) = make_double2(t0, t1);
+                next_tile<NT>(i, j);
+            }
+            for (int q = 0; q < d; ++q) {
+                double sL = 0.0;
+                i = 0;
+                j = 0;
+#pragma unroll 1
+                for (int s = 0; s < NTRI; ++s) {
+                    const double2 tt = *reinterpret_cast<const double2*>(m.tiles + s * 64 + cst);
+                    const double xr = m.xL[q * NP + 8 * i + g];
+                    const double2 xc = *reinterpret_cast<const double2*>(m.xL + q * NP + 8 * j + 2 * t);
+                    const double d0 = xr - xc.x, d1 = xr - xc.y;
+                    sL = fma(tt.x * d0, d0, sL);
+                    sL = fma(tt.y * d1, d1, sL);
+                    next_tile<NT>(i, j);
+                }
+                sL = warp_sum(sL);
+                if (lane == 0) m.red[1 + q] = sL;
+            }
+        }
+        {
+            const double a0 = warp_sum(s_rho), a1 = warp_sum(s_vL), a2 = warp_sum(s_dg);
+            if (lane == 0) {
+                m.red[0] = a0;
+                m.red[1 + d] = a1;
+                m.red[3 + 2 * d] = a2;
+            }
+        }
+        __syncwarp();
+        for (int q = lane; q < nq; q += 32) {
+            double f = 1.0;
+            if (q == 0) f = 1.0 / rho;
+            else if (q <= d) f = m.inv[q - 1];
+            else if (q == d + 1) f = 1.0 / vL;
+            else if (q <= 2 * d + 1) f = m.inv[d + (q - d - 2)];
+            else if (q == 2 * d + 2) f = 1.0 / vD;
+            p.grad[(size_t)prob * nq + q] = -0.5 * f * m.red[q];  // d(nlml) = -1/2 sum G dK
+        }
+        __syncwarp();
+    }
+}
+
+template <int NT, int DS>
+int launch_v4(cudaStream_t st, const SmallArgs& a) {
+    const int wd = (int)((WarpMem<NT>::doubles(a.d) + 1) & ~(size_t)1);  // every warp's base stays 16-byte aligned
+    const size_t bytes = (size_t)wd * 8 * WPC;
+    static int attr_bytes = -1, ctas_per_sm = 0, sms = 0;
+    if ((int)bytes != attr_bytes) {
+        if (cudaFuncSetAttribute(gpr_small_v4_kernel<NT, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+            return -2;
+        cudaFuncSetAttribute(gpr_small_v4_kernel<NT, DS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, gpr_small_v4_kernel<NT, DS>, WPC * 32, bytes) != cudaSuccess ||
+            ctas_per_sm < 1)
+            return -2;
+        attr_bytes = (int)bytes;
+    }
+    const int want = (a.B + WPC - 1) / WPC, cap = sms * ctas_per_sm;
+    gpr_small_v4_kernel<NT, DS><<<want < cap ? want : cap, WPC * 32, bytes, st>>>(a, wd);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+template <int NT>
+int launch_nt(cudaStream_t st, const SmallArgs& a) {
+    return a.d == 5 ? launch_v4<NT, 5>(st, a) : launch_v4<NT, 0>(st, a);
+}
+
+}  // namespace
+
+int launch_gpr_small_v4(cudaStream_t st, const SmallArgs& a) {
+    if (a.N < 1 || a.N > 64 || a.d < 1 || a.d > MFGP_SMALL_MAX_D) return -1;
+    if (a.B <= 0) return 0;
+    switch ((a.N + 7) / 8) {
+        case 1: return launch_nt<1>(st, a);
+        case 2: return launch_nt<2>(st, a);
+        case 3: return launch_nt<3>(st, a);
+        case 4: return launch_nt<4>(st, a);
+        case 5: return launch_nt<5>(st, a);
+        case 6: return launch_nt<6>(st, a);
+        case 7: return launch_nt<7>(st, a);
+        default: return launch_nt<8>(st, a);
+    }
+}
