@@ -94,8 +94,8 @@ struct WarpMem {
 // K^L C-fragment of tile (i, j): rows 8i+g, columns 8j+2t, 8j+2t+1.  Expanded-square distance folded into the
 // exponent; log(var_L) is split over the two row terms.  With DS > 0 the scaled coordinates are returned for reuse.
 template <int NT, int DS>
-__device__ __forceinline__ void kl_tile(const WarpMem<NT>& m, int d, int i, int j, int g, int t, double& k0, double& k1,
-                                        double* xr, double* xc0, double* xc1) {
+__device__ __forceinline__ void kl_tile(const WarpMem<NT>& m, const double* etab, int d, int i, int j, int g, int t, double& k0,
+                                        double& k1, double* xr, double* xc0, double* xc1) {
     constexpr int NP = 8 * NT;
     const int r = 8 * i + g, c = 8 * j + 2 * t;
     double e0 = 0.0, e1 = 0.0;
@@ -121,8 +121,8 @@ __device__ __forceinline__ void kl_tile(const WarpMem<NT>& m, int d, int i, int 
     const double2 hr = *reinterpret_cast<const double2*>(m.hs + 2 * r);
     const double2 h0 = *reinterpret_cast<const double2*>(m.hs + 2 * c);
     const double2 h1 = *reinterpret_cast<const double2*>(m.hs + 2 * c + 2);
-    k0 = (hr.y * h0.y) * fexp(e0 + (hr.x + h0.x));
-    k1 = (hr.y * h1.y) * fexp(e1 + (hr.x + h1.x));
+    k0 = (hr.y * h0.y) * fexp_tab(e0 + (hr.x + h0.x), etab);
+    k1 = (hr.y * h1.y) * fexp_tab(e1 + (hr.x + h1.x), etab);
 }
 
 template <int NT>
@@ -140,7 +140,10 @@ __global__ void __launch_bounds__(WPC * 32, 3) gpr_small_v4_kernel(SmallArgs p, 
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = p.N, d = (DS > 0) ? DS : p.d;
-    const WarpMem<NT> m(smem + (size_t)warp * warp_doubles, d);
+    const double* etab = smem;  // 2^(j/64), shared by the CTA
+    fexp_table_fill(smem, threadIdx.x, WPC * 32);
+    __syncthreads();
+    const WarpMem<NT> m(smem + 64 + (size_t)warp * warp_doubles, d);
     const int g = lane >> 2, t = lane & 3;
     const int cst = tile_off(g, 2 * t);                                // C fragment: row g, cols 2t, 2t+1
     const int km0 = tile_off(g, t), km1 = tile_off(g, t + 4);          // K-major fragment: (row g, col t + 4s)
@@ -194,8 +197,8 @@ __global__ void __launch_bounds__(WPC * 32, 3) gpr_small_v4_kernel(SmallArgs p, 
                 const int ib = two ? i : ia, jb = two ? j : ja;
                 next_tile<NT>(i, j);
                 double ka0, ka1, kb0, kb1;
-                kl_tile<NT, 0>(m, d, ia, ja, g, t, ka0, ka1, nullptr, nullptr, nullptr);
-                kl_tile<NT, 0>(m, d, ib, jb, g, t, kb0, kb1, nullptr, nullptr, nullptr);
+                kl_tile<NT, 0>(m, etab, d, ia, ja, g, t, ka0, ka1, nullptr, nullptr, nullptr);
+                kl_tile<NT, 0>(m, etab, d, ib, jb, g, t, kb0, kb1, nullptr, nullptr, nullptr);
                 if (ia == ja) {  // diagonal: + noise (real rows) or identity (padding rows keep the factorisation well posed)
                     const double dg = (8 * ia + g < N) ? noise : 1.0;
                     if (g == 2 * t) ka0 += dg;
@@ -224,13 +227,14 @@ __global__ void __launch_bounds__(WPC * 32, 3) gpr_small_v4_kernel(SmallArgs p, 
                 const double df = (p.X[(size_t)ri * (d + 1) + q] - p.X[(size_t)rj * (d + 1) + q]) * m.inv[d + q];
                 ee = fma(df, df, ee);
             }
-            m.tiles[cslot_rt<NT>(ri >> 3, rj >> 3) * 64 + tile_off(ri & 7, rj & 7)] += vD * fexp(-0.5 * ee);
+            m.tiles[cslot_rt<NT>(ri >> 3, rj >> 3) * 64 + tile_off(ri & 7, rj & 7)] += vD * fexp_tab(-0.5 * ee, etab);
         }
         __syncwarp();
 
         // ---- 2: left-looking tile Cholesky ------------------------------------------------------------
         int bad = 0;
-        double logdet2 = 0.0;
+        double lmant = 1.0;  // prod(pivots) = lmant * 2^lexp, renormalised after every diagonal tile
+        int lexp = 0;
         {
 #pragma unroll 1
             for (int kb = 0; kb < NT; ++kb) {
@@ -285,15 +289,15 @@ __global__ void __launch_bounds__(WPC * 32, 3) gpr_small_v4_kernel(SmallArgs p, 
                             a[r][2 * c2 + 1] = v.y;
                         }
                     double prod = 1.0;
+                    int hiv[8], hmin = 0x7fffffff, hmax = 0;  // pivot sign / NaN test on the high words (integer pipe)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        double piv = a[j][j];
-                        if (!(piv > 0.0)) {
-                            if (!bad) bad = 8 * kb + j + 1;
-                            piv = nan("");
-                        }
+                        const double piv = a[j][j];
+                        hiv[j] = __double2hiint(piv);
+                        hmin = min(hmin, hiv[j]);
+                        hmax = max(hmax, hiv[j]);
                         prod *= piv;
-                        const double ri = rsqrt(piv);
+                        const double ri = frsqrt(piv);
                         rinv[j] = ri;
 #pragma unroll
                         for (int i = j + 1; i < 8; ++i) a[i][j] *= ri;
@@ -302,7 +306,19 @@ __global__ void __launch_bounds__(WPC * 32, 3) gpr_small_v4_kernel(SmallArgs p, 
 #pragma unroll
                             for (int i = k; i < 8; ++i) a[i][k] = fma(-a[i][j], a[k][j], a[i][k]);
                     }
-                    logdet2 += log(prod);
+                    if (hmin <= 0 || hmax >= 0x7ff00000) {  // a pivot <= 0 (or denormal), inf or NaN: report the first one
+                        if (!bad) {
+#pragma unroll
+                            for (int j = 7; j >= 0; --j)
+                                if (hiv[j] <= 0 || hiv[j] >= 0x7ff00000) bad = 8 * kb + j + 1;
+                        }
+                        prod = nan("");
+                    }
+                    {
+                        const int ph = __double2hiint(prod);
+                        lexp += ((ph >> 20) & 0x7ff) - 1023;
+                        lmant *= __hiloint2double((ph & 0x800fffff) | 0x3ff00000, __double2loint(prod));
+                    }
                     const int c = lane & 7;  // column c of inv(L_kk) by forward substitution
                     double w[8];
 #pragma unroll
@@ -406,6 +422,7 @@ __global__ void __launch_bounds__(WPC * 32, 3) gpr_small_v4_kernel(SmallArgs p, 
             }
             quad = warp_sum(quad);
             if (lane == 0) {
+                const double logdet2 = log(lmant) + 0.69314718055994530942 * (double)lexp;  // sum log(pivot) = 2 sum log L_ii
                 p.nlml[prob] = 0.5 * quad + 0.5 * logdet2 + 0.5 * N * LOG2PI;
                 if (p.info) p.info[prob] = bad;
                 if (bad) atomicCAS(p.d_info, 0, bad);
@@ -477,7 +494,7 @@ __global__ void __launch_bounds__(WPC * 32, 3) gpr_small_v4_kernel(SmallArgs p, 
                     const double df = (p.X[(size_t)ri * (d + 1) + q] - p.X[(size_t)rj * (d + 1) + q]) * m.inv[d + q];
                     ee = fma(df, df, ee);
                 }
-                td = m.tiles[cslot_rt<NT>(ri >> 3, rj >> 3) * 64 + tile_off(ri & 7, rj & 7)] * vD * fexp(-0.5 * ee);
+                td = m.tiles[cslot_rt<NT>(ri >> 3, rj >> 3) * 64 + tile_off(ri & 7, rj & 7)] * vD * fexp_tab(-0.5 * ee, etab);
             }
             const double sv = warp_sum(td);
             if (lane == 0) m.red[2 + 2 * d] += sv;
@@ -502,8 +519,8 @@ __global__ void __launch_bounds__(WPC * 32, 3) gpr_small_v4_kernel(SmallArgs p, 
                 next_tile<NT>(i, j);
                 double ka0, ka1, kb0, kb1;
                 double xra[DS], xa0[DS], xa1[DS], xrb[DS], xb0[DS], xb1[DS];
-                kl_tile<NT, DS>(m, d, ia, ja, g, t, ka0, ka1, xra, xa0, xa1);
-                kl_tile<NT, DS>(m, d, ib, jb, g, t, kb0, kb1, xrb, xb0, xb1);
+                kl_tile<NT, DS>(m, etab, d, ia, ja, g, t, ka0, ka1, xra, xa0, xa1);
+                kl_tile<NT, DS>(m, etab, d, ib, jb, g, t, kb0, kb1, xrb, xb0, xb1);
                 const double2 ga = *reinterpret_cast<const double2*>(m.tiles + s * 64 + cst);
                 double2 gb = *reinterpret_cast<const double2*>(m.tiles + (two ? s + 1 : s) * 64 + cst);
                 if (!two) gb.x = gb.y = 0.0;
@@ -534,7 +551,7 @@ __global__ void __launch_bounds__(WPC * 32, 3) gpr_small_v4_kernel(SmallArgs p, 
 #pragma unroll 1
             for (int s = 0; s < NTRI; ++s) {
                 double k0, k1;
-                kl_tile<NT, 0>(m, d, i, j, g, t, k0, k1, nullptr, nullptr, nullptr);
+                kl_tile<NT, 0>(m, etab, d, i, j, g, t, k0, k1, nullptr, nullptr, nullptr);
                 const double2 gg = *reinterpret_cast<const double2*>(m.tiles + s * 64 + cst);
                 const double t0 = gg.x * k0, t1 = gg.y * k1;
                 const double hr = (double)((hfmask >> (8 * i + g)) & 1ull);
@@ -587,7 +604,7 @@ __global__ void __launch_bounds__(WPC * 32, 3) gpr_small_v4_kernel(SmallArgs p, 
 template <int NT, int DS>
 int launch_v4(cudaStream_t st, const SmallArgs& a) {
     const int wd = (int)((WarpMem<NT>::doubles(a.d) + 1) & ~(size_t)1);  // every warp's base stays 16-byte aligned
-    const size_t bytes = (size_t)wd * 8 * WPC;
+    const size_t bytes = (size_t)wd * 8 * WPC + 64 * 8;
     static int attr_bytes = -1, ctas_per_sm = 0, sms = 0;
     if ((int)bytes != attr_bytes) {
         if (cudaFuncSetAttribute(gpr_small_v4_kernel<NT, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
