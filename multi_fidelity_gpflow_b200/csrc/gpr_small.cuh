@@ -19,6 +19,7 @@ struct SmallArgs {
     int* info;            // [B] or nullptr
     int* d_info;          // handle-wide first failure
     int NP;               // filled by the launcher
+    double* scratch;      // v4: K^L of every problem in flight (L2-resident), filled by the launcher
 };
 int launch_gpr_small(cudaStream_t s, const SmallArgs& a);      // v1: one CTA per problem (DFMA)
 int launch_gpr_small_mma(cudaStream_t s, const SmallArgs& a);  // v2: one warp per problem (DMMA tiles)

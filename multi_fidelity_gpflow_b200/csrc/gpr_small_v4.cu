@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(WPC * 32, 3) gpr_small_v4_kernel(SmallArgs p, 
     const int km0 = tile_off(g, t), km1 = tile_off(g, t + 4);          // K-major fragment: (row g, col t + 4s)
     const int mm0 = tile_off(t, g), mm1 = tile_off(t + 4, g);          // M-major fragment: (row t + 4s, col g)
     const int nq = 2 * d + 4;
+    double* scr = p.scratch + ((size_t)blockIdx.x * WPC + warp) * (NTRI * 64) + 2 * lane;
 
     for (int prob = blockIdx.x * WPC + warp; prob < p.B; prob += gridDim.x * WPC) {
         // ---- setup --------------------------------------------------------------------------------
@@ -199,6 +200,10 @@ __global__ void __launch_bounds__(WPC * 32, 3) gpr_small_v4_kernel(SmallArgs p, 
                 double ka0, ka1, kb0, kb1;
                 kl_tile<NT, 0>(m, etab, d, ia, ja, g, t, ka0, ka1, nullptr, nullptr, nullptr);
                 kl_tile<NT, 0>(m, etab, d, ib, jb, g, t, kb0, kb1, nullptr, nullptr, nullptr);
+                if (p.grad) {  // K^L is needed again by the gradient: park it in the L2-resident scratch (own lane's values)
+                    __stcg(reinterpret_cast<double2*>(scr + s * 64), make_double2(ka0, ka1));
+                    if (two) __stcg(reinterpret_cast<double2*>(scr + (s + 1) * 64), make_double2(kb0, kb1));
+                }
                 if (ia == ja) {  // diagonal: + noise (real rows) or identity (padding rows keep the factorisation well posed)
                     const double dg = (8 * ia + g < N) ? noise : 1.0;
                     if (g == 2 * t) ka0 += dg;
@@ -510,6 +515,8 @@ __global__ void __launch_bounds__(WPC * 32, 3) gpr_small_v4_kernel(SmallArgs p, 
 #pragma unroll
             for (int q = 0; q < DS; ++q) sL[q] = 0.0;
             int i = 0, j = 0;
+            double2 kna = __ldcg(reinterpret_cast<const double2*>(scr));
+            double2 knb = __ldcg(reinterpret_cast<const double2*>(scr + (NTRI > 1 ? 64 : 0)));
 #pragma unroll 1
             for (int s = 0; s < NTRI; s += 2) {
                 const int ia = i, ja = j;
@@ -517,23 +524,32 @@ __global__ void __launch_bounds__(WPC * 32, 3) gpr_small_v4_kernel(SmallArgs p, 
                 const bool two = (s + 1 < NTRI);
                 const int ib = two ? i : ia, jb = two ? j : ja;
                 next_tile<NT>(i, j);
-                double ka0, ka1, kb0, kb1;
-                double xra[DS], xa0[DS], xa1[DS], xrb[DS], xb0[DS], xb1[DS];
-                kl_tile<NT, DS>(m, etab, d, ia, ja, g, t, ka0, ka1, xra, xa0, xa1);
-                kl_tile<NT, DS>(m, etab, d, ib, jb, g, t, kb0, kb1, xrb, xb0, xb1);
+                const double2 ka = kna, kb = knb;
+                if (s + 2 < NTRI) kna = __ldcg(reinterpret_cast<const double2*>(scr + (s + 2) * 64));
+                if (s + 3 < NTRI) knb = __ldcg(reinterpret_cast<const double2*>(scr + (s + 3) * 64));
                 const double2 ga = *reinterpret_cast<const double2*>(m.tiles + s * 64 + cst);
                 double2 gb = *reinterpret_cast<const double2*>(m.tiles + (two ? s + 1 : s) * 64 + cst);
                 if (!two) gb.x = gb.y = 0.0;
-                const double ta0 = ga.x * ka0, ta1 = ga.y * ka1, tb0 = gb.x * kb0, tb1 = gb.y * kb1;
-                // exponent of rho in s_i s_j: number of HF points in the pair (s == rho exactly on HF rows)
-                const double hra = (double)((hfmask >> (8 * ia + g)) & 1ull), hrb = (double)((hfmask >> (8 * ib + g)) & 1ull);
-                const double hca0 = (double)((hfmask >> (8 * ja + 2 * t)) & 1ull), hca1 = (double)((hfmask >> (8 * ja + 2 * t + 1)) & 1ull);
-                const double hcb0 = (double)((hfmask >> (8 * jb + 2 * t)) & 1ull), hcb1 = (double)((hfmask >> (8 * jb + 2 * t + 1)) & 1ull);
+                const double ta0 = ga.x * ka.x, ta1 = ga.y * ka.y, tb0 = gb.x * kb.x, tb1 = gb.y * kb.y;
                 s_vL += (ta0 + ta1) + (tb0 + tb1);
-                s_rho += ta0 * (hra + hca0) + ta1 * (hra + hca1) + tb0 * (hrb + hcb0) + tb1 * (hrb + hcb1);
+                // exponent of rho in s_i s_j = number of HF points in the pair; only tiles that touch an HF row or column
+                if ((((hfmask >> (8 * ia)) | (hfmask >> (8 * ja))) & 0xffull) != 0ull) {
+                    const double hr = (double)((hfmask >> (8 * ia + g)) & 1ull);
+                    const double hc0 = (double)((hfmask >> (8 * ja + 2 * t)) & 1ull), hc1 = (double)((hfmask >> (8 * ja + 2 * t + 1)) & 1ull);
+                    s_rho += ta0 * (hr + hc0) + ta1 * (hr + hc1);
+                }
+                if ((((hfmask >> (8 * ib)) | (hfmask >> (8 * jb))) & 0xffull) != 0ull) {
+                    const double hr = (double)((hfmask >> (8 * ib + g)) & 1ull);
+                    const double hc0 = (double)((hfmask >> (8 * jb + 2 * t)) & 1ull), hc1 = (double)((hfmask >> (8 * jb + 2 * t + 1)) & 1ull);
+                    s_rho += tb0 * (hr + hc0) + tb1 * (hr + hc1);
+                }
+                const int ra = 8 * ia + g, ca = 8 * ja + 2 * t, rb = 8 * ib + g, cb = 8 * jb + 2 * t;
 #pragma unroll
                 for (int q = 0; q < DS; ++q) {
-                    const double da0 = xra[q] - xa0[q], da1 = xra[q] - xa1[q], db0 = xrb[q] - xb0[q], db1 = xrb[q] - xb1[q];
+                    const double xra = m.xL[q * NP + ra], xrb = m.xL[q * NP + rb];
+                    const double2 xa = *reinterpret_cast<const double2*>(m.xL + q * NP + ca);
+                    const double2 xb = *reinterpret_cast<const double2*>(m.xL + q * NP + cb);
+                    const double da0 = xra - xa.x, da1 = xra - xa.y, db0 = xrb - xb.x, db1 = xrb - xb.y;
                     sL[q] = fma(ta0 * da0, da0, sL[q]);
                     sL[q] = fma(ta1 * da1, da1, sL[q]);
                     sL[q] = fma(tb0 * db0, db0, sL[q]);
@@ -550,10 +566,9 @@ __global__ void __launch_bounds__(WPC * 32, 3) gpr_small_v4_kernel(SmallArgs p, 
             int i = 0, j = 0;
 #pragma unroll 1
             for (int s = 0; s < NTRI; ++s) {
-                double k0, k1;
-                kl_tile<NT, 0>(m, etab, d, i, j, g, t, k0, k1, nullptr, nullptr, nullptr);
+                const double2 kk = __ldcg(reinterpret_cast<const double2*>(scr + s * 64));
                 const double2 gg = *reinterpret_cast<const double2*>(m.tiles + s * 64 + cst);
-                const double t0 = gg.x * k0, t1 = gg.y * k1;
+                const double t0 = gg.x * kk.x, t1 = gg.y * kk.y;
                 const double hr = (double)((hfmask >> (8 * i + g)) & 1ull);
                 const double hc0 = (double)((hfmask >> (8 * j + 2 * t)) & 1ull), hc1 = (double)((hfmask >> (8 * j + 2 * t + 1)) & 1ull);
                 s_vL += t0 + t1;
@@ -619,8 +634,16 @@ int launch_v4(cudaStream_t st, const SmallArgs& a) {
         attr_bytes = (int)bytes;
     }
     const int want = (a.B + WPC - 1) / WPC, cap = sms * ctas_per_sm;
-    gpr_small_v4_kernel<NT, DS><<<want < cap ? want : cap, WPC * 32, bytes, st>>>(a, wd);
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    const int grid = want < cap ? want : cap;
+    SmallArgs b = a;
+    b.scratch = nullptr;
+    if (a.grad) {  // one K^L slot per resident warp: <= 148 * 12 * 14 KB = 25 MB, stays in the 126 MB L2
+        if (cudaMallocAsync(&b.scratch, (size_t)grid * WPC * WarpMem<NT>::NTRI * 64 * sizeof(double), st) != cudaSuccess) return -2;
+    }
+    gpr_small_v4_kernel<NT, DS><<<grid, WPC * 32, bytes, st>>>(b, wd);
+    const bool ok = cudaGetLastError() == cudaSuccess;
+    if (b.scratch) cudaFreeAsync(b.scratch, st);
+    return ok ? 0 : -2;
 }
 
 template <int NT>
