@@ -18,6 +18,7 @@
 #include "mathx.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace {
 
@@ -36,6 +37,7 @@ struct TileSmem {
     double* hb;  // [64] h_b
     double* th;  // [2d+3] theta, then [2d] inverse length-scales (L then D)
     int* flags;  // [2] any HF row / any HF col
+    double* etab;  // [64] 2^(j/64) for fexp_tab
 };
 
 __device__ inline TileSmem carve(double* base, int d) {
@@ -55,10 +57,11 @@ __device__ inline TileSmem carve(double* base, int d) {
     t.hb = t.ga + T;
     t.th = t.hb + T;
     t.flags = reinterpret_cast<int*>(t.th + 4 * MFGP_MAX_D + 4);
+    t.etab = t.th + 4 * MFGP_MAX_D + 4 + 2;
     return t;
 }
 
-__host__ __device__ inline size_t tile_smem_bytes(int d) { return (size_t)(4 * d * COV_TILE + 8 * COV_TILE + 4 * MFGP_MAX_D + 4) * 8 + 16; }
+__host__ __device__ inline size_t tile_smem_bytes(int d) { return (size_t)(4 * d * COV_TILE + 8 * COV_TILE + 4 * MFGP_MAX_D + 4) * 8 + 16 + 64 * 8; }
 
 // Loads theta and both 64-point tiles.  Must be called by all 256 threads.
 __device__ inline void load_tiles(const TileSmem& t, const double* __restrict__ Xa, int Na, int i0,
@@ -68,6 +71,7 @@ __device__ inline void load_tiles(const TileSmem& t, const double* __restrict__ 
     const int T = COV_TILE;
     if (tid < 2 * d + 3) t.th[tid] = theta[tid];
     if (tid < 2) t.flags[tid] = 0;
+    fexp_table_fill(t.etab, tid, blockDim.x);
     __syncthreads();
     if (tid < 2 * d) {
         // inverse length-scales: th[2d+3 + k] = 1/lsL[k], th[3d+3 + k] = 1/lsD[k]
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(256, 2) cov_kernel(CovArgs p, int TJ, int vec_
         for (int c = 0; c < 4; ++c) {
             const int cc = col_of(tx, c);
             // (s_a s_b) and (h_a + h_b) are commutative: K(X,X) comes out exactly symmetric
-            val[a][c] = (t.fa[r0 + a] * t.sb[cc]) * vL * fexp(acc[a][c] + (t.haL[r0 + a] + t.hbL[cc]));
+            val[a][c] = (t.fa[r0 + a] * t.sb[cc]) * vL * fexp_tab(acc[a][c] + (t.haL[r0 + a] + t.hbL[cc]), t.etab);
         }
     if (t.flags[0] && t.flags[1]) {  // tile touches the HF x HF block: add the discrepancy GP
         tile_dots(t.aD, t.bD, p.d, r0, tx, acc);
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(256, 2) cov_kernel(CovArgs p, int TJ, int vec_
             for (int c = 0; c < 4; ++c) {
                 const int cc = col_of(tx, c);
                 const double g = t.ga[r0 + a] * t.hb[cc];
-                if (g != 0.0) val[a][c] += g * fexp(acc[a][c] + (t.haD[r0 + a] + t.hbD[cc]));
+                if (g != 0.0) val[a][c] += g * fexp_tab(acc[a][c] + (t.haD[r0 + a] + t.hbD[cc]), t.etab);
             }
     }
     if (p.symmetric && I == J) {
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(256, 2) cov_grad_kernel(CovGradArgs p, int TJ,
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int cc = col_of(tx, c);
-            const double kl = (t.fa[r0 + a] * t.sb[cc]) * vL * fexp(acc[a][c] + (t.haL[r0 + a] + t.hbL[cc]));
+            const double kl = (t.fa[r0 + a] * t.sb[cc]) * vL * fexp_tab(acc[a][c] + (t.haL[r0 + a] + t.hbL[cc]), t.etab);
             const double v = TL[a][c] * kl;  // G_ij * K^L_ij
             TL[a][c] = v;
             s_vL += v;
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(256, 2) cov_grad_kernel(CovGradArgs p, int TJ,
             for (int c = 0; c < 4; ++c) {
                 const int cc = col_of(tx, c);
                 const double g = t.ga[r0 + a] * t.hb[cc];
-                const double v = (g != 0.0) ? TD[a][c] * g * fexp(acc[a][c] + (t.haD[r0 + a] + t.hbD[cc])) : 0.0;
+                const double v = (g != 0.0) ? TD[a][c] * g * fexp_tab(acc[a][c] + (t.haD[r0 + a] + t.hbD[cc]), t.etab) : 0.0;
                 TD[a][c] = v;
                 s_vD += v;
             }
@@ -433,22 +437,282 @@ __global__ void cov_grad_reduce_kernel(const double* __restrict__ partial, long 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K1 streaming variant (large problems).  Profile of the one-tile-per-CTA kernel above at N = 16 384 (profiles/
+// r01_ncu_cov_*): each CTA spends ~1/3 of its life in a serial prologue (theta -> 1/ls -> scale 128 points, three
+// barriers, two dependent global round trips) that 2 resident CTAs cannot hide, so neither the FP64 pipe (48 %) nor
+// HBM (24-42 %) is busy.  Here the per-point work is done ONCE by cov_prescale_kernel into a k-major workspace
+//     P[k][Npad]:  k < d: x/ls_L | k < 2d: x/ls_delta | 2d: -|x/ls_L|^2/2 + log(var_L)/2 | 2d+1: -|x/ls_d|^2/2 + log(var_d)/2
+//                  | 2d+2: s in {0,1,rho} | 2d+3: h in {0,1}
+// and persistent CTAs walk a contiguous range of tiles, double-buffering the two 64-point panels of the NEXT tile
+// with cp.async while the current tile is evaluated and stored.
+// ---------------------------------------------------------------------------------------------
+__global__ void cov_prescale_kernel(const double* __restrict__ X, int N, int Npad, int d, const double* __restrict__ theta,
+                                    long theta_stride, double* __restrict__ P, unsigned char* __restrict__ tflags) {
+    const int b = blockIdx.y;
+    const double* th = theta + (long)b * theta_stride;
+    const int S = 2 * d + 4;
+    double* Pb = P + (long)b * S * Npad;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;  // blockDim.x == COV_TILE: one block per tile
+    double s = 0.0, h = 0.0;
+    bool live = false;
+    if (p < N) {
+        const double fid = X[(long)p * (d + 1) + d];
+        if (fid == 0.0) {
+            s = 1.0;
+            live = true;
+        } else if (fid == 1.0) {
+            s = th[0];
+            h = 1.0;
+            live = true;
+        }
+    }
+    double nL = 0.0, nD = 0.0;
+    for (int k = 0; k < d; ++k) {
+        const double x = live ? X[(long)p * (d + 1) + k] : 0.0;
+        const double xl = x / th[1 + k], xd = x / th[2 + d + k];
+        Pb[(long)k * Npad + p] = xl;
+        Pb[(long)(d + k) * Npad + p] = xd;
+        nL = fma(xl, xl, nL);
+        nD = fma(xd, xd, nD);
+    }
+    Pb[(long)(2 * d) * Npad + p] = fma(-0.5, nL, 0.5 * log(th[1 + d]));
+    Pb[(long)(2 * d + 1) * Npad + p] = fma(-0.5, nD, 0.5 * log(th[2 + 2 * d]));
+    Pb[(long)(2 * d + 2) * Npad + p] = s;
+    Pb[(long)(2 * d + 3) * Npad + p] = h;
+    // per-tile flags: bit 0 = some HF point, bit 1 = some row scale != 1 (HF with rho != 1, dead or padding rows)
+    const int any_h = __syncthreads_or(h != 0.0), any_s = __syncthreads_or(s != 1.0);
+    if (threadIdx.x == 0) tflags[(long)b * gridDim.x + blockIdx.x] = (unsigned char)((any_h ? 1 : 0) | (any_s ? 2 : 0));
+}
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(src));
+}
+
+struct CovStreamArgs {
+    const double* Pa;  // [batch][S][Napad]
+    const double* Pb;  // [batch][S][Nbpad]
+    const unsigned char* fa;  // [batch][TI]
+    const unsigned char* fb;  // [batch][TJ]
+    int Na, Nb, Napad, Nbpad, d, TI, TJ;
+    long ntiles;  // per batch
+    long total;   // batch * ntiles
+    long per_cta;
+    double* K;
+    long ldk, strideK;
+    int symmetric, mirror, vec_ok;
+    double diag_add;
+    const double* diag_add_vec;
+};
+
+__global__ void __launch_bounds__(256, 2) cov_stream_kernel(CovStreamArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    const int d = p.d, S = 2 * d + 4, T = COV_TILE;
+    const int panel = S * T;             // doubles per 64-point panel
+    double* etab = smem;                 // [64]
+    double* stage0 = smem + 64;          // stage s: [a panel | b panel]
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int tx = (w & 1) * 8 + (lane & 7);
+    const int ty = (w >> 1) * 4 + (lane >> 3);
+    const int r0 = ty * 4;
+    fexp_table_fill(etab, tid, blockDim.x);
+
+    const long w0 = (long)blockIdx.x * p.per_cta;
+    long w1 = w0 + p.per_cta;
+    if (w1 > p.total) w1 = p.total;
+    if (w0 >= w1) return;
+
+    auto decode = [&](long wi, int& b, int& I, int& J) {
+        b = (int)(wi / p.ntiles);
+        tile_index(wi - (long)b * p.ntiles, p.TJ, p.symmetric, I, J);
+    };
+    auto issue = [&](int stage, int b, int I, int J) {
+        double* sa = stage0 + (size_t)stage * 2 * panel;
+        double* sb = sa + panel;
+        const double* ga = p.Pa + (long)b * S * p.Napad + (long)I * T;
+        const double* gb = p.Pb + (long)b * S * p.Nbpad + (long)J * T;
+        const int chunks = S * (T / 2);  // 16-byte chunks per panel
+        for (int c = tid; c < chunks; c += 256) {
+            const int k = c / (T / 2), o = (c % (T / 2)) * 2;
+            cp_async16(sa + k * T + o, ga + (long)k * p.Napad + o);
+            cp_async16(sb + k * T + o, gb + (long)k * p.Nbpad + o);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+
+    int b, I, J;
+    decode(w0, b, I, J);
+    issue(0, b, I, J);
+    int stage = 0;
+    for (long wi = w0; wi < w1; ++wi) {
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();  // current stage landed for everyone; the other stage is no longer being read
+        int nb = b, nI = I, nJ = J;
+        if (wi + 1 < w1) {
+            decode(wi + 1, nb, nI, nJ);
+            issue(stage ^ 1, nb, nI, nJ);
+        }
+        const double* A = stage0 + (size_t)stage * 2 * panel;
+        const double* B = A + panel;
+        const int fla = p.fa[(long)b * p.TI + I], flb = p.fb[(long)b * p.TJ + J];
+
+        double acc[4][4], val[4][4];
+        tile_dots(A, B, d, r0, tx, acc);
+        {
+            const double* hA = A + 2 * d * T;
+            const double* hB = B + 2 * d * T;
+            const double2 ha01 = *reinterpret_cast<const double2*>(hA + r0), ha23 = *reinterpret_cast<const double2*>(hA + r0 + 2);
+            const double2 hb01 = *reinterpret_cast<const double2*>(hB + 2 * tx), hb23 = *reinterpret_cast<const double2*>(hB + 32 + 2 * tx);
+            const double ha[4] = {ha01.x, ha01.y, ha23.x, ha23.y}, hb[4] = {hb01.x, hb01.y, hb23.x, hb23.y};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) val[a][c] = fexp_tab(acc[a][c] + (ha[a] + hb[c]), etab);
+        }
+        if ((fla | flb) & 2) {  // some row scale differs from 1: (s_a s_b) is commutative -> K(X,X) exactly symmetric
+            const double* sA = A + (2 * d + 2) * T;
+            const double* sB = B + (2 * d + 2) * T;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) val[a][c] *= sA[r0 + a] * sB[col_of(tx, c)];
+        }
+        if ((fla & 1) && (flb & 1)) {  // tile touches the HF x HF block: add the discrepancy GP
+            tile_dots(A + d * T, B + d * T, d, r0, tx, acc);
+            const double* hA = A + (2 * d + 1) * T;
+            const double* hB = B + (2 * d + 1) * T;
+            const double* gA = A + (2 * d + 3) * T;
+            const double* gB = B + (2 * d + 3) * T;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int cc = col_of(tx, c);
+                    if (gA[r0 + a] * gB[cc] != 0.0) val[a][c] += fexp_tab(acc[a][c] + (hA[r0 + a] + hB[cc]), etab);
+                }
+        }
+        const int i0 = I * T, j0 = J * T;
+        if (p.symmetric && I == J) {
+            const double dg = p.diag_add_vec ? p.diag_add_vec[b] : p.diag_add;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (r0 + a == col_of(tx, c)) val[a][c] += dg;
+        }
+        double* __restrict__ K = p.K + (long)b * p.strideK;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = i0 + r0 + a;
+            if (i >= p.Na) continue;
+#pragma unroll
+            for (int hblk = 0; hblk < 2; ++hblk) {
+                const int j = j0 + hblk * 32 + 2 * tx;
+                double* dst = K + (long)i * p.ldk + j;
+                if (p.vec_ok && j + 1 < p.Nb) {
+                    *reinterpret_cast<double2*>(dst) = make_double2(val[a][2 * hblk], val[a][2 * hblk + 1]);
+                } else {
+                    if (j < p.Nb) dst[0] = val[a][2 * hblk];
+                    if (j + 1 < p.Nb) dst[1] = val[a][2 * hblk + 1];
+                }
+            }
+        }
+        if (p.symmetric && p.mirror && I != J) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int j = j0 + col_of(tx, c);
+                if (j >= p.Nb) continue;
+                const int i = i0 + r0;
+                double* dst = K + (long)j * p.ldk + i;
+                if (p.vec_ok && i + 3 < p.Na) {
+                    *reinterpret_cast<double2*>(dst) = make_double2(val[0][c], val[1][c]);
+                    *reinterpret_cast<double2*>(dst + 2) = make_double2(val[2][c], val[3][c]);
+                } else {
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+                        if (i + a < p.Na) dst[a] = val[a][c];
+                }
+            }
+        }
+        b = nb;
+        I = nI;
+        J = nJ;
+        stage ^= 1;
+    }
+}
+
 }  // namespace
 
 static bool aligned16(const void* p) { return (reinterpret_cast<size_t>(p) & 15) == 0; }
+
+static int launch_cov_stream(cudaStream_t s, const CovArgs& a, int TI, int TJ, long ntiles, int vec_ok) {
+    const int S = 2 * a.d + 4, T = COV_TILE;
+    const int Napad = TI * T, Nbpad = TJ * T;
+    const bool same = a.symmetric || (a.Xa == a.Xb && a.Na == a.Nb);
+    const size_t pa = (size_t)a.batch * S * Napad, pb = same ? 0 : (size_t)a.batch * S * Nbpad;
+    const size_t fbytes = (((size_t)a.batch * (TI + (same ? 0 : TJ))) + 15) & ~(size_t)15;
+    double* ws = nullptr;
+    if (cudaMallocAsync(&ws, (pa + pb) * sizeof(double) + fbytes, s) != cudaSuccess) return -2;
+    unsigned char* fl = reinterpret_cast<unsigned char*>(ws + pa + pb);
+    cov_prescale_kernel<<<dim3(TI, a.batch), T, 0, s>>>(a.Xa, a.Na, Napad, a.d, a.theta, a.theta_stride, ws, fl);
+    if (!same)
+        cov_prescale_kernel<<<dim3(TJ, a.batch), T, 0, s>>>(a.Xb, a.Nb, Nbpad, a.d, a.theta, a.theta_stride, ws + pa,
+                                                            fl + (size_t)a.batch * TI);
+    CovStreamArgs q{};
+    q.Pa = ws;
+    q.Pb = same ? ws : ws + pa;
+    q.fa = fl;
+    q.fb = same ? fl : fl + (size_t)a.batch * TI;
+    q.Na = a.Na; q.Nb = a.Nb; q.Napad = Napad; q.Nbpad = same ? Napad : Nbpad; q.d = a.d; q.TI = TI; q.TJ = same ? TI : TJ;
+    if (!a.symmetric) q.TJ = TJ;
+    q.ntiles = ntiles;
+    q.total = ntiles * a.batch;
+    q.K = a.K; q.ldk = a.ldk; q.strideK = a.strideK;
+    q.symmetric = a.symmetric; q.mirror = a.mirror; q.vec_ok = vec_ok;
+    q.diag_add = a.diag_add; q.diag_add_vec = a.diag_add_vec;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const size_t smem = (size_t)(64 + 4 * S * T) * sizeof(double);
+    static size_t attr = 0;
+    if (smem > attr) {
+        if (cudaFuncSetAttribute(cov_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaFreeAsync(ws, s);
+            return -2;
+        }
+        attr = smem;
+    }
+    // contiguous chunks of tiles per CTA: ~8 chunks per resident CTA slot keeps the tail short
+    long per = (q.total + (long)sms * 2 * 8 - 1) / ((long)sms * 2 * 8);
+    if (per < 1) per = 1;
+    if (per > 64) per = 64;
+    q.per_cta = per;
+    const long grid = (q.total + per - 1) / per;
+    cov_stream_kernel<<<(unsigned)grid, 256, smem, s>>>(q);
+    const bool ok = cudaGetLastError() == cudaSuccess;
+    cudaFreeAsync(ws, s);
+    return ok ? 0 : -2;
+}
 
 int launch_cov(cudaStream_t s, const CovArgs& a) {
     if (a.d < 1 || a.d > MFGP_MAX_D) return -1;
     if (a.Na <= 0 || a.Nb <= 0 || a.batch <= 0) return 0;
     const int TI = (a.Na + COV_TILE - 1) / COV_TILE, TJ = (a.Nb + COV_TILE - 1) / COV_TILE;
     const long ntiles = a.symmetric ? (long)TI * (TI + 1) / 2 : (long)TI * TJ;
+    const int vec_ok = aligned16(a.K) && (a.ldk % 2 == 0) && (a.strideK % 2 == 0);
+    static const int stream_min = [] { const char* e = getenv("MFGP_COV_STREAM_MIN_TILES"); return e ? atoi(e) : 1024; }();
+    if (ntiles * a.batch >= stream_min) return launch_cov_stream(s, a, TI, TJ, ntiles, vec_ok);
     const size_t smem = tile_smem_bytes(a.d);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(MFGP_MAX_D));
         attr_set = true;
     }
-    const int vec_ok = aligned16(a.K) && (a.ldk % 2 == 0) && (a.strideK % 2 == 0);
     dim3 grid((unsigned)ntiles, 1, a.batch);
     cov_kernel<<<grid, 256, smem, s>>>(a, TJ, vec_ok);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
