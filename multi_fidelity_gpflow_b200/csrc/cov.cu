@@ -513,6 +513,8 @@ __global__ void __launch_bounds__(256, 2) cov_stream_kernel(CovStreamArgs p) {
     const int panel = S * T;             // doubles per 64-point panel
     double* etab = smem;                 // [64]
     double* stage0 = smem + 64;          // stage s: [a panel | b panel]
+    constexpr int MROW = 18;             // staging row stride (16 values + 2 pad: 16-byte aligned rows, fewer bank conflicts)
+    double* mstage = stage0 + 4 * panel; // [8 warps][32][MROW] transposed blocks of the mirrored tile
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int tx = (w & 1) * 8 + (lane & 7);
     const int ty = (w >> 1) * 4 + (lane >> 3);
@@ -524,39 +526,56 @@ __global__ void __launch_bounds__(256, 2) cov_stream_kernel(CovStreamArgs p) {
     if (w1 > p.total) w1 = p.total;
     if (w0 >= w1) return;
 
-    auto decode = [&](long wi, int& b, int& I, int& J) {
-        b = (int)(wi / p.ntiles);
-        tile_index(wi - (long)b * p.ntiles, p.TJ, p.symmetric, I, J);
+    // walk the tiles of this CTA in linear order (row-major; lower triangle when symmetric) without re-decoding
+    auto advance = [&](int& b, int& I, int& J) {
+        ++J;
+        if (p.symmetric ? (J > I) : (J == p.TJ)) {
+            J = 0;
+            if (++I == p.TI) {
+                I = 0;
+                ++b;
+            }
+        }
     };
+    // cp.async work split: thread -> (panel row k0 + 8m, 16-byte chunk o); constant across tiles
+    const int ck0 = tid >> 5, co = (tid & 31) * 2;
     auto issue = [&](int stage, int b, int I, int J) {
-        double* sa = stage0 + (size_t)stage * 2 * panel;
+        double* sa = stage0 + (size_t)stage * 2 * panel + ck0 * T + co;
         double* sb = sa + panel;
-        const double* ga = p.Pa + (long)b * S * p.Napad + (long)I * T;
-        const double* gb = p.Pb + (long)b * S * p.Nbpad + (long)J * T;
-        const int chunks = S * (T / 2);  // 16-byte chunks per panel
-        for (int c = tid; c < chunks; c += 256) {
-            const int k = c / (T / 2), o = (c % (T / 2)) * 2;
-            cp_async16(sa + k * T + o, ga + (long)k * p.Napad + o);
-            cp_async16(sb + k * T + o, gb + (long)k * p.Nbpad + o);
+        const double* ga = p.Pa + (long)b * S * p.Napad + (long)I * T + (long)ck0 * p.Napad + co;
+        const double* gb = p.Pb + (long)b * S * p.Nbpad + (long)J * T + (long)ck0 * p.Nbpad + co;
+        for (int k = ck0; k < S; k += 8) {
+            cp_async16(sa, ga);
+            cp_async16(sb, gb);
+            sa += 8 * T;
+            sb += 8 * T;
+            ga += 8 * (long)p.Napad;
+            gb += 8 * (long)p.Nbpad;
         }
         asm volatile("cp.async.commit_group;\n" ::);
     };
 
     int b, I, J;
-    decode(w0, b, I, J);
+    {
+        b = (int)(w0 / p.ntiles);
+        tile_index(w0 - (long)b * p.ntiles, p.TJ, p.symmetric, I, J);
+    }
     issue(0, b, I, J);
+    int nfla = p.fa[(long)b * p.TI + I], nflb = p.fb[(long)b * p.TJ + J];
     int stage = 0;
     for (long wi = w0; wi < w1; ++wi) {
         asm volatile("cp.async.wait_group 0;\n" ::);
         __syncthreads();  // current stage landed for everyone; the other stage is no longer being read
+        const int fla = nfla, flb = nflb;
         int nb = b, nI = I, nJ = J;
         if (wi + 1 < w1) {
-            decode(wi + 1, nb, nI, nJ);
+            advance(nb, nI, nJ);
             issue(stage ^ 1, nb, nI, nJ);
+            nfla = p.fa[(long)nb * p.TI + nI];  // consumed one tile later: the load latency is off the critical path
+            nflb = p.fb[(long)nb * p.TJ + nJ];
         }
         const double* A = stage0 + (size_t)stage * 2 * panel;
         const double* B = A + panel;
-        const int fla = p.fa[(long)b * p.TI + I], flb = p.fb[(long)b * p.TJ + J];
 
         double acc[4][4], val[4][4];
         tile_dots(A, B, d, r0, tx, acc);
@@ -603,36 +622,70 @@ __global__ void __launch_bounds__(256, 2) cov_stream_kernel(CovStreamArgs p) {
                     if (r0 + a == col_of(tx, c)) val[a][c] += dg;
         }
         double* __restrict__ K = p.K + (long)b * p.strideK;
+        if (p.vec_ok && i0 + T <= p.Na && j0 + T <= p.Nb) {  // interior tile: unguarded 128-bit stores
+            double* dst = K + (long)(i0 + r0) * p.ldk + j0 + 2 * tx;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int i = i0 + r0 + a;
-            if (i >= p.Na) continue;
+            for (int a = 0; a < 4; ++a) {
+                *reinterpret_cast<double2*>(dst) = make_double2(val[a][0], val[a][1]);
+                *reinterpret_cast<double2*>(dst + 32) = make_double2(val[a][2], val[a][3]);
+                dst += p.ldk;
+            }
+            if (p.symmetric && p.mirror && I != J) {
+                // Mirrored tile: a direct STG of the transposed 4x4 blocks touches 8 half-filled lines per instruction and
+                // backs up the LSU.  Instead each warp transposes its 16 x 32 block through a private staging buffer and
+                // every lane hands ONE full 128-byte row to the bulk-copy engine (cp.async.bulk, asynchronous, no registers).
+                double* M = mstage + w * (32 * MROW);
+                asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // previous tile's rows have left the buffer
+                __syncwarp();
+                const int lx = lane & 7, ly = lane >> 3;
 #pragma unroll
-            for (int hblk = 0; hblk < 2; ++hblk) {
-                const int j = j0 + hblk * 32 + 2 * tx;
-                double* dst = K + (long)i * p.ldk + j;
-                if (p.vec_ok && j + 1 < p.Nb) {
-                    *reinterpret_cast<double2*>(dst) = make_double2(val[a][2 * hblk], val[a][2 * hblk + 1]);
-                } else {
-                    if (j < p.Nb) dst[0] = val[a][2 * hblk];
-                    if (j + 1 < p.Nb) dst[1] = val[a][2 * hblk + 1];
+                for (int c = 0; c < 4; ++c) {
+                    double* q = M + ((c >> 1) * 16 + 2 * lx + (c & 1)) * MROW + 4 * ly;
+                    *reinterpret_cast<double2*>(q) = make_double2(val[0][c], val[1][c]);
+                    *reinterpret_cast<double2*>(q + 2) = make_double2(val[2][c], val[3][c]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                __syncwarp();
+                {
+                    const int col = (lane >> 4) * 32 + (w & 1) * 16 + (lane & 15);
+                    double* dst = K + (long)(j0 + col) * p.ldk + i0 + 16 * (w >> 1);
+                    const unsigned src = (unsigned)__cvta_generic_to_shared(M + lane * MROW);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;\n" ::"l"(dst), "r"(src) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
                 }
             }
-        }
-        if (p.symmetric && p.mirror && I != J) {
+        } else {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int j = j0 + col_of(tx, c);
-                if (j >= p.Nb) continue;
-                const int i = i0 + r0;
-                double* dst = K + (long)j * p.ldk + i;
-                if (p.vec_ok && i + 3 < p.Na) {
-                    *reinterpret_cast<double2*>(dst) = make_double2(val[0][c], val[1][c]);
-                    *reinterpret_cast<double2*>(dst + 2) = make_double2(val[2][c], val[3][c]);
-                } else {
+            for (int a = 0; a < 4; ++a) {
+                const int i = i0 + r0 + a;
+                if (i >= p.Na) continue;
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
-                        if (i + a < p.Na) dst[a] = val[a][c];
+                for (int hblk = 0; hblk < 2; ++hblk) {
+                    const int j = j0 + hblk * 32 + 2 * tx;
+                    double* dst = K + (long)i * p.ldk + j;
+                    if (p.vec_ok && j + 1 < p.Nb) {
+                        *reinterpret_cast<double2*>(dst) = make_double2(val[a][2 * hblk], val[a][2 * hblk + 1]);
+                    } else {
+                        if (j < p.Nb) dst[0] = val[a][2 * hblk];
+                        if (j + 1 < p.Nb) dst[1] = val[a][2 * hblk + 1];
+                    }
+                }
+            }
+            if (p.symmetric && p.mirror && I != J) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int j = j0 + col_of(tx, c);
+                    if (j >= p.Nb) continue;
+                    const int i = i0 + r0;
+                    double* dst = K + (long)j * p.ldk + i;
+                    if (p.vec_ok && i + 3 < p.Na) {
+                        *reinterpret_cast<double2*>(dst) = make_double2(val[0][c], val[1][c]);
+                        *reinterpret_cast<double2*>(dst + 2) = make_double2(val[2][c], val[3][c]);
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < 4; ++a)
+                            if (i + a < p.Na) dst[a] = val[a][c];
+                    }
                 }
             }
         }
@@ -641,6 +694,7 @@ __global__ void __launch_bounds__(256, 2) cov_stream_kernel(CovStreamArgs p) {
         J = nJ;
         stage ^= 1;
     }
+    asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // shared memory must outlive the bulk copies that read it
 }
 
 }  // namespace
@@ -678,7 +732,7 @@ static int launch_cov_stream(cudaStream_t s, const CovArgs& a, int TI, int TJ, l
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const size_t smem = (size_t)(64 + 4 * S * T) * sizeof(double);
+    const size_t smem = (size_t)(64 + 4 * S * T + 8 * 32 * 18) * sizeof(double);
     static size_t attr = 0;
     if (smem > attr) {
         if (cudaFuncSetAttribute(cov_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
