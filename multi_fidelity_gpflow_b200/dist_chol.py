@@ -1,98 +1,316 @@
-"""Distributed exact-GP NLML for ONE large problem across the GPUs of a box.
+"""Distributed exact-GP NLML for ONE large problem across the GPUs of a box (BASELINE config 5).
 
-Round-1 form: 1-D block-cyclic by block COLUMNS (width `nbd`), right-looking:
-    owner(k): assemble-on-the-fly is done up front by every rank for its own block columns from the
-              replicated X (no communication); then per step
-              potrf + inverse of the diagonal block, panel solve  (mfgp_potrf_inv, mfgp_gemm)
-    all     : panel broadcast (NCCL over NVLink, torch.distributed.broadcast)
-    all     : trailing update of the block columns they own       (mfgp_gemm, DMMA)
-followed by a distributed forward substitution for a = L^-1 y (the owner of block k broadcasts
-[a_k ; L[k+1:,k] a_k]).  The 2-D grid with look-ahead is the round-2 step.  All device arithmetic goes
-through libmfgp.so on torch CUDA tensors; torch is only buffers + NCCL."""
+Layout: 2-D block-cyclic.  The N x N covariance is cut into nb x nb blocks; block (i, j), i >= j, lives on the rank
+at grid position (i mod P, j mod Q) of a P x Q process grid (8 GPUs: 2 x 4).  Every rank assembles its own blocks from
+the replicated inputs with the fused covariance kernel (no communication), then the right-looking Cholesky runs
+
+    step k   diag owner        : L_kk, W_kk = L_kk^-1            (mfgp_potrf_inv)        -> broadcast W_kk
+             column k mod Q    : L_ik = A_ik W_kk^T  (local rows) (mfgp_gemm, DMMA)       -> P panel broadcasts (NVLink)
+             everyone          : A_ij -= L_ik L_jk^T for the local blocks i >= j > k      (mfgp_gemm, DMMA)
+             everyone          : a_k = W_kk y_k ; y[k+1:] -= L[k+1:, k] a_k               (replicated, O(N nb))
+
+with LOOK-AHEAD: block column k+1 is updated, factored and broadcast on a second CUDA stream while the main stream
+is still applying panel k to the rest of the trailing matrix, so the latency-bound panel step and the NVLink transfers
+hide behind the DMMA GEMMs.  NLML = 1/2 |a|^2 + sum log L_ii + N/2 log 2 pi  (GPflow GPR.log_marginal_likelihood,
+reference call sites mfgpflow/linear.py:206,227).  P = 1 gives the 1-D block-cyclic column layout of round 1.
+
+All device arithmetic goes through libmfgp.so (`GpuOps`); torch supplies buffers, streams and NCCL.  The block
+operations are behind a four-method interface so that the schedule (ownership, broadcasts, look-ahead ordering) is
+also exercised on CPU by a world-size-2/4 gloo test with a NumPy double (tests/test_dist_chol_cpu.py) -- that double
+lives in tests/, the product path has no CPU fallback."""
 from __future__ import annotations
 
-import ctypes as C
 import math
 
 import numpy as np
 
-from . import _lib
+
+def process_grid(world: int) -> tuple[int, int]:
+    """P x Q with P <= Q, both as close to sqrt(world) as the factorisation allows (8 -> 2 x 4, 4 -> 2 x 2, 2 -> 1 x 2)."""
+    p = int(math.isqrt(world))
+    while world % p:
+        p -= 1
+    return p, world // p
 
 
-def distributed_gpr_nlml(handle, X, Y, theta, noise, nbd=512, group=None):
-    """Every rank passes the same host X [N, d+1], Y [N, 1], theta, noise.  Returns the NLML (same on all ranks)."""
+class GpuOps:
+    """Block operations on torch CUDA tensors through the C-ABI (include/mfgp.h)."""
+
+    def __init__(self, handle):
+        import torch
+
+        from . import _lib
+
+        self.torch, self._lib, self.h = torch, _lib, handle
+        self.L = _lib._lib
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        handle.set_async(True)
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise self._lib.MFGPError(f"{what}: rc={rc}: {self.L.mfgp_last_error(self.h._h).decode()}")
+
+    # -- streams ---------------------------------------------------------------------------------------
+    def new_stream(self):
+        return self.torch.cuda.Stream()
+
+    def use(self, stream):
+        """Context manager: torch's current stream AND the library's stream."""
+        ops = self
+
+        class _Ctx:
+            def __enter__(self_inner):
+                self_inner.ctx = ops.torch.cuda.stream(stream)
+                self_inner.ctx.__enter__()
+                ops.h.set_stream(stream.cuda_stream)
+
+            def __exit__(self_inner, *exc):
+                return self_inner.ctx.__exit__(*exc)
+
+        return _Ctx()
+
+    def record(self, stream):
+        ev = self.torch.cuda.Event()
+        ev.record(stream)
+        return ev
+
+    def wait(self, stream, event):
+        if event is not None:
+            stream.wait_event(event)
+
+    def finish(self):
+        self.torch.cuda.synchronize()
+        self.h.set_async(False)
+        info = self.h.sync()
+        self.h.set_stream(None)
+        if info:
+            raise self._lib.NotPositiveDefiniteError(f"distributed potrf: pivot {info} of a diagonal block not positive")
+
+    # -- block arithmetic -------------------------------------------------------------------------------
+    def cov(self, Xa, Xb, theta, out):
+        ptr = self._lib._ptr
+        self._chk(self.L.mfgp_cov(self.h._h, ptr(Xa), Xa.shape[0], ptr(Xb), Xb.shape[0], Xa.shape[1] - 1, ptr(theta), ptr(out),
+                                  out.stride(0)), "cov")
+
+    def potrf_inv(self, A, W):
+        ptr = self._lib._ptr
+        self._chk(self.L.mfgp_potrf_inv(self.h._h, ptr(A), A.shape[0], A.stride(0), ptr(W), W.stride(0)), "potrf_inv")
+
+    def gemm(self, ta, tb, m, n, k, alpha, A, B, beta, C):
+        ptr = self._lib._ptr
+        self._chk(self.L.mfgp_gemm(self.h._h, b"T" if ta else b"N", b"T" if tb else b"N", m, n, k, float(alpha), ptr(A),
+                                   A.stride(0), ptr(B), B.stride(0), float(beta), ptr(C), C.stride(0)), "gemm")
+
+
+def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None, grid=None, lookahead=True, profile=None):
+    """Every rank passes the same host X [N, d+1], Y [N, 1], theta [2d+3], noise.  Returns the NLML (same on all ranks).
+
+    `handle_or_ops`: a `_lib.Handle` (product path) or an object with GpuOps' interface (CPU schedule tests).
+    `profile`: optional dict; when given every phase is bracketed by a device synchronize and its wall time is
+    accumulated there (serialises the two streams -- for diagnosis only)."""
+    import time
+
     import torch
     import torch.distributed as dist
 
-    L = _lib._lib
+    class _Phase:
+        def __init__(self, name):
+            self.name = name
+
+        def __enter__(self):
+            if profile is not None:
+                torch.cuda.synchronize()
+                self.t0 = time.perf_counter()
+
+        def __exit__(self, *exc):
+            if profile is not None:
+                torch.cuda.synchronize()
+                profile[self.name] = profile.get(self.name, 0.0) + time.perf_counter() - self.t0
+
+    ops = handle_or_ops if hasattr(handle_or_ops, "potrf_inv") else GpuOps(handle_or_ops)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    dev = torch.device("cuda", torch.cuda.current_device())
+    P, Q = grid if grid is not None else process_grid(world)
+    if P * Q != world:
+        raise ValueError(f"process grid {P}x{Q} does not match world size {world}")
+    p, q = rank // Q, rank % Q
+    dev = ops.device
     X = np.ascontiguousarray(X, dtype=np.float64)
-    N, d = X.shape[0], X.shape[1] - 1
-    assert Y.shape[1] == 1, "single-output problem (SURVEY config C5)"
-    nblk = (N + nbd - 1) // nbd
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    N0, d = X.shape[0], X.shape[1] - 1
+    if Y.ndim != 2 or Y.shape[1] != 1:
+        raise ValueError("single-output problem expected (SURVEY config C5)")
+    nb = int(nbd)
+    if nb % 2:
+        raise ValueError("block size must be even (16-byte aligned rows)")
+    nblk = (N0 + nb - 1) // nb
+    N = nblk * nb
+    npad = N - N0
+    # padding rows: fidelity 2.0 -> zero covariance (reference linear.py:82), noise on the diagonal, y = 0;
+    # they add npad * log(noise)/2 to sum log L_ii, removed at the end
+    if npad:
+        Xp = np.zeros((N, d + 1))
+        Xp[:N0] = X
+        Xp[N0:, d] = 2.0
+        Yp = np.zeros((N, 1))
+        Yp[:N0] = Y
+        X, Y = Xp, Yp
     Xd = torch.from_numpy(X).to(dev)
     thd = torch.from_numpy(np.ascontiguousarray(theta, dtype=np.float64)).to(dev)
-    y = torch.zeros(N, 2, dtype=torch.float64, device=dev)  # column 1 is padding (even leading dimension for the GEMM)
-    y[:, 0] = torch.from_numpy(np.ascontiguousarray(Y[:, 0], dtype=np.float64)).to(dev)
-    ptr = _lib._ptr
-    h = handle._h
-    stream = torch.cuda.current_stream()
-    handle.set_stream(stream.cuda_stream)
-    handle.set_async(True)
+    y = torch.zeros(N, 2, dtype=torch.float64, device=dev)  # column 1 pads the leading dimension to an even number
+    y[:, 0] = torch.from_numpy(Y[:, 0].copy()).to(dev)
 
-    def chk(rc, what):
-        if rc != 0:
-            raise _lib.MFGPError(f"{what}: rc={rc}: {L.mfgp_last_error(h).decode()}")
+    R = [i for i in range(nblk) if i % P == p]   # local block rows
+    Cb = [j for j in range(nblk) if j % Q == q]  # local block columns
 
-    # ---- assembly: block column j (rows j*nbd.., width wj) = K(X[rows], X[cols]) + noise on its diagonal ----
-    cols = {}
-    for j in range(rank, nblk, world):
-        r0, wj = j * nbd, min(nbd, N - j * nbd)
-        A = torch.empty(N - r0, nbd, dtype=torch.float64, device=dev)
-        chk(L.mfgp_cov(h, ptr(Xd[r0:]), N - r0, ptr(Xd[r0:r0 + wj]), wj, d, ptr(thd), ptr(A), nbd), "cov")
-        A[:wj, :wj].diagonal().add_(noise)
-        cols[j] = A
-    logdet = torch.zeros(1, dtype=torch.float64, device=dev)
-    panel = torch.empty(N, nbd, dtype=torch.float64, device=dev)
-    Wk = torch.empty(nbd, nbd, dtype=torch.float64, device=dev)
-    avec = torch.zeros(N, dtype=torch.float64, device=dev)
-    msg = torch.zeros(N, 2, dtype=torch.float64, device=dev)
-    for k in range(nblk):
-        r0, wk = k * nbd, min(nbd, N - k * nbd)
-        own = k % world
-        rows = N - r0
-        if rank == own:
-            A = cols[k]
-            # diagonal block: L_kk (in place) and W_kk = L_kk^-1
-            chk(L.mfgp_potrf_inv(h, ptr(A), wk, nbd, ptr(Wk), nbd), "potrf_inv")
-            logdet += torch.log(A[:wk, :wk].diagonal()).sum()
-            if rows > wk:  # panel rows below: L_ik = A_ik W_kk^T (in place: one 128-wide column tile per CTA row)
-                tmp = torch.empty(rows - wk, nbd, dtype=torch.float64, device=dev)
-                chk(L.mfgp_gemm(h, b"N", b"T", rows - wk, wk, wk, 1.0, ptr(A[wk:]), nbd, ptr(Wk), nbd, 0.0, ptr(tmp), nbd), "panel")
-                A[wk:, :wk] = tmp[:, :wk]
-            panel[:rows].copy_(A)
-            # forward substitution piece: a_k = W_kk y_k ; u = L[k+1:, k] a_k
-            chk(L.mfgp_gemm(h, b"N", b"N", wk, 2, wk, 1.0, ptr(Wk), nbd, ptr(y[r0:]), 2, 0.0, ptr(msg), 2), "a_k")
-            if rows > wk:
-                chk(L.mfgp_gemm(h, b"N", b"N", rows - wk, 2, wk, 1.0, ptr(A[wk:]), nbd, ptr(msg), 2, 0.0, ptr(msg[wk:]), 2), "u")
-        dist.broadcast(panel[:rows], src=own, group=group)
-        dist.broadcast(msg[:rows], src=own, group=group)
-        avec[r0:r0 + wk] = msg[:wk, 0]
-        if rows > wk:
-            y[r0 + wk:, 0] -= msg[wk:rows, 0]
-        # trailing update of the owned block columns j > k:  A_j -= P[j rows] P[j block rows]^T
-        for j in range(k + 1, nblk):
-            if j % world != rank:
+    def first_local_row(j):  # index into R of the first local block row >= j
+        return max(0, -(-(j - p) // P))
+
+    # Streams and buffers are created once per (N, nb, grid) and kept on the ops object -- like the library handle's own
+    # workspaces -- so that repeated evaluations (an optimiser loop) allocate nothing: cudaMalloc/cudaFree of the
+    # multi-GB block columns would otherwise serialise the device and dominate the call.
+    cache = getattr(ops, "_dist_chol_ws", None)
+    key = (N, nb, P, Q, d, str(dev))
+    if cache is None or cache.get("key") != key:
+        cache = {"key": key, "s_main": ops.new_stream(), "s_pan": ops.new_stream(), "cols": {}}
+        for j in Cb:
+            nr = len(R) - first_local_row(j)
+            if nr > 0:
+                cache["cols"][j] = torch.empty(nr * nb, nb, dtype=torch.float64, device=dev)
+        cache["pans"] = [torch.empty(max(nblk - 1, 1) * nb, nb, dtype=torch.float64, device=dev) for _ in range(2)]
+        cache["Wks"] = [torch.empty(nb, nb, dtype=torch.float64, device=dev) for _ in range(2)]
+        cache["piece"] = torch.empty(((nblk + P - 1) // P) * nb, nb, dtype=torch.float64, device=dev)
+        cache["Rloc"] = torch.empty(max(len(R), 1) * nb, nb, dtype=torch.float64, device=dev)
+        cache["Xr"] = torch.empty(max(len(R), 1) * nb, d + 1, dtype=torch.float64, device=dev)
+        try:
+            ops._dist_chol_ws = cache
+        except AttributeError:
+            pass
+    s_main, s_pan = cache["s_main"], cache["s_pan"]
+
+    # ---- assembly (no communication) -------------------------------------------------------------------
+    cols = cache["cols"]
+    with ops.use(s_main), _Phase("assembly"):
+        Xr = cache["Xr"]
+        if R:
+            Xr[:len(R) * nb].view(len(R), nb, d + 1).copy_(Xd.view(nblk, nb, d + 1)[p::P])
+        for j in Cb:
+            f = first_local_row(j)
+            nr = len(R) - f
+            if nr <= 0:
                 continue
-            o = (j - k) * nbd
-            wj = min(nbd, N - j * nbd)
-            chk(L.mfgp_gemm(h, b"N", b"T", rows - o, wj, wk, -1.0, ptr(panel[o:]), nbd, ptr(panel[o:]), nbd, 1.0,
-                            ptr(cols[j]), nbd), "update")
-    handle.set_async(False)
-    info = handle.sync()
-    if info:
-        raise _lib.NotPositiveDefiniteError(f"distributed potrf: pivot {info} not positive")
-    dist.all_reduce(logdet, group=group)
-    quad = float((avec * avec).sum().item())
-    return 0.5 * quad + float(logdet.item()) + 0.5 * N * math.log(2.0 * math.pi)
+            A = cols[j]
+            ops.cov(Xr[f * nb:len(R) * nb], Xd[j * nb:(j + 1) * nb], thd, A)
+            if R[f] == j:
+                A[:nb].diagonal().add_(noise)
+    ev_main = ops.record(s_main)
+
+    logdet = torch.zeros(1, dtype=torch.float64, device=dev)
+    quad = torch.zeros(1, dtype=torch.float64, device=dev)
+    pans, Wks, piece, Rloc = cache["pans"], cache["Wks"], cache["piece"], cache["Rloc"]
+    ak = torch.zeros(nb, 2, dtype=torch.float64, device=dev)
+    ev_pan = [None, None]
+
+    def apply_panel(k, j, pan, stream_rows):
+        """A_j -= L[rows >= j, k] L[j, k]^T on the local rows (stream_rows: panel rows of the local block rows > k)."""
+        if j not in cols:
+            return
+        f = first_local_row(j)
+        fk = first_local_row(k + 1)
+        m = (len(R) - f) * nb
+        if m <= 0:
+            return
+        ops.gemm(False, True, m, nb, nb, -1.0, stream_rows[(f - fk) * nb:], pan[(j - k - 1) * nb:(j - k) * nb], 1.0, cols[j])
+
+    def gather_local_rows(k, pan, out):
+        """out <- panel rows of the local block rows > k, contiguous (strided block slice of the global-order panel)."""
+        fk = first_local_row(k + 1)
+        n = len(R) - fk
+        if n > 0:
+            s0 = R[fk] - (k + 1)
+            out[:n * nb].view(n, nb, nb).copy_(pan[:(nblk - k - 1) * nb].view(nblk - k - 1, nb, nb)[s0::P])
+        return out
+
+    def factor_panel(k, buf):
+        """Runs on s_pan: diagonal block, panel solve and the broadcasts of step k into pans[buf] / Wks[buf]."""
+        kp, kq = k % P, k % Q
+        pan, Wk = pans[buf], Wks[buf]
+        mine = (q == kq) and (k in cols)
+        with _Phase("diag_potrf_inv"):
+            if q == kq and p == kp:
+                A = cols[k]
+                ops.potrf_inv(A[:nb], Wk)
+                logdet.add_(torch.log(A[:nb].diagonal()).sum())
+        with _Phase("bcast_W"):
+            dist.broadcast(Wk, src=kp * Q + kq, group=group)
+        nbelow = nblk - k - 1
+        if nbelow == 0:
+            return
+        with _Phase("panel_solve"):
+            if mine:
+                A = cols[k]
+                off = nb if p == kp else 0
+                m = A.shape[0] - off
+                if m > 0:
+                    tmp = piece[:m]
+                    ops.gemm(False, True, m, nb, nb, 1.0, A[off:], Wk, 0.0, tmp)
+                    A[off:].copy_(tmp)
+        for pp in range(P):  # one broadcast per process row of column kq: rows i > k, i = pp (mod P)
+            i0 = k + 1 + ((pp - (k + 1)) % P)
+            if i0 >= nblk:
+                continue
+            cnt = (nblk - 1 - i0) // P + 1
+            src = pp * Q + kq
+            if rank == src:
+                off = nb if pp == kp else 0
+                buf_t = cols[k][off:off + cnt * nb]
+            else:
+                buf_t = piece[:cnt * nb]
+            with _Phase("bcast_panel"):
+                dist.broadcast(buf_t, src=src, group=group)
+                pan[:nbelow * nb].view(nbelow, nb, nb)[i0 - (k + 1)::P].copy_(buf_t.view(cnt, nb, nb))
+
+    with ops.use(s_pan):
+        ops.wait(s_pan, ev_main)
+        factor_panel(0, 0)
+        ev_pan[0] = ops.record(s_pan)
+
+    for k in range(nblk):
+        buf = k % 2
+        pan, Wk = pans[buf], Wks[buf]
+        nbelow = nblk - k - 1
+        nxt = k + 1
+        if lookahead and nxt < nblk:
+            with ops.use(s_pan):
+                ops.wait(s_pan, ev_main)  # column k+1 carries every update up to panel k-1; buffer (k+1)%2 is free again
+                with _Phase("lookahead_update"):
+                    if nxt in cols:
+                        rows_pan = gather_local_rows(k, pan, piece)  # `piece` is idle between the broadcasts of two steps
+                        apply_panel(k, nxt, pan, rows_pan)
+                factor_panel(nxt, nxt % 2)
+                ev_pan[nxt % 2] = ops.record(s_pan)
+        with ops.use(s_main):
+            ops.wait(s_main, ev_pan[buf])
+            # a_k = W_kk y_k ; y[k+1:] -= L[k+1:, k] a_k   (replicated on every rank)
+            with _Phase("forward_subst"):
+                ops.gemm(False, False, nb, 2, nb, 1.0, Wk, y[k * nb:(k + 1) * nb], 0.0, ak)
+                quad.add_((ak[:, 0] * ak[:, 0]).sum())
+                if nbelow:
+                    ops.gemm(False, False, nbelow * nb, 2, nb, -1.0, pan, ak, 1.0, y[(k + 1) * nb:])
+            with _Phase("trailing_update"):
+                if nbelow:
+                    rows_pan = gather_local_rows(k, pan, Rloc)
+                    for j in Cb:
+                        if j > k and not (lookahead and j == nxt):
+                            apply_panel(k, j, pan, rows_pan)
+            ev_main = ops.record(s_main)
+        if not lookahead and nxt < nblk:
+            with ops.use(s_pan):
+                ops.wait(s_pan, ev_main)
+                factor_panel(nxt, nxt % 2)
+                ev_pan[nxt % 2] = ops.record(s_pan)
+    with ops.use(s_main):
+        ops.wait(s_main, ev_pan[(nblk - 1) % 2])
+        dist.all_reduce(logdet, group=group)
+    ops.finish()
+    ld = float(logdet.item()) - (0.5 * npad * math.log(noise) if npad else 0.0)
+    return 0.5 * float(quad.item()) + ld + 0.5 * N0 * math.log(2.0 * math.pi)
