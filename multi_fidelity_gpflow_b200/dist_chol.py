@@ -9,9 +9,11 @@ the replicated inputs with the fused covariance kernel (no communication), then 
              everyone          : A_ij -= L_ik L_jk^T for the local blocks i >= j > k      (mfgp_gemm, DMMA)
              everyone          : a_k = W_kk y_k ; y[k+1:] -= L[k+1:, k] a_k               (replicated, O(N nb))
 
-with LOOK-AHEAD: block column k+1 is updated, factored and broadcast on a second CUDA stream while the main stream
-is still applying panel k to the rest of the trailing matrix, so the latency-bound panel step and the NVLink transfers
-hide behind the DMMA GEMMs.  NLML = 1/2 |a|^2 + sum log L_ii + N/2 log 2 pi  (GPflow GPR.log_marginal_likelihood,
+with LOOK-AHEAD on three CUDA streams: the CRITICAL stream factors the diagonal block, broadcasts its inverse, solves
+and broadcasts only the single block (k+1, k) and completes the next diagonal block, so potrf(k+1) starts ~0.3 ms after
+potrf(k) ends; the PANEL stream solves and broadcasts the bulk of panel k and updates block column k+1; the MAIN stream
+applies panel k to the rest of the trailing matrix.  Critical and bulk broadcasts use two communicators so that a small
+broadcast never queues behind a 100 MB panel.  NLML = 1/2 |a|^2 + sum log L_ii + N/2 log 2 pi  (GPflow GPR.log_marginal_likelihood,
 reference call sites mfgpflow/linear.py:206,227).  P = 1 gives the 1-D block-cyclic column layout of round 1.
 
 All device arithmetic goes through libmfgp.so (`GpuOps`); torch supplies buffers, streams and NCCL.  The block
@@ -51,8 +53,9 @@ class GpuOps:
             raise self._lib.MFGPError(f"{what}: rc={rc}: {self.L.mfgp_last_error(self.h._h).decode()}")
 
     # -- streams ---------------------------------------------------------------------------------------
-    def new_stream(self):
-        return self.torch.cuda.Stream()
+    def new_stream(self, high_priority=False):
+        # the panel stream is high priority: its small GEMMs / potrf must not queue behind the trailing update's CTAs
+        return self.torch.cuda.Stream(priority=-1 if high_priority else 0)
 
     def use(self, stream):
         """Context manager: torch's current stream AND the library's stream."""
@@ -171,13 +174,14 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
     cache = getattr(ops, "_dist_chol_ws", None)
     key = (N, nb, P, Q, d, str(dev))
     if cache is None or cache.get("key") != key:
-        cache = {"key": key, "s_main": ops.new_stream(), "s_pan": ops.new_stream(), "cols": {}}
+        cache = {"key": key, "s_main": ops.new_stream(), "s_pan": ops.new_stream(True), "s_crit": ops.new_stream(True), "cols": {}}
         for j in Cb:
             nr = len(R) - first_local_row(j)
             if nr > 0:
                 cache["cols"][j] = torch.empty(nr * nb, nb, dtype=torch.float64, device=dev)
         cache["pans"] = [torch.empty(max(nblk - 1, 1) * nb, nb, dtype=torch.float64, device=dev) for _ in range(2)]
         cache["Wks"] = [torch.empty(nb, nb, dtype=torch.float64, device=dev) for _ in range(2)]
+        cache["blks"] = [torch.empty(nb, nb, dtype=torch.float64, device=dev) for _ in range(2)]
         cache["piece"] = torch.empty(((nblk + P - 1) // P) * nb, nb, dtype=torch.float64, device=dev)
         cache["Rloc"] = torch.empty(max(len(R), 1) * nb, nb, dtype=torch.float64, device=dev)
         cache["Xr"] = torch.empty(max(len(R), 1) * nb, d + 1, dtype=torch.float64, device=dev)
@@ -185,7 +189,15 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
             ops._dist_chol_ws = cache
         except AttributeError:
             pass
-    s_main, s_pan = cache["s_main"], cache["s_pan"]
+    if lookahead:
+        s_main, s_pan, s_crit = cache["s_main"], cache["s_pan"], cache["s_crit"]
+        if cache.get("crit_group") is None:  # second communicator: critical-path broadcasts never queue behind a panel
+            ranks = dist.get_process_group_ranks(group if group is not None else dist.group.WORLD)
+            cache["crit_group"] = dist.new_group(ranks=ranks)
+        crit_group = cache["crit_group"]
+    else:  # reference schedule: the same steps, one stream, one communicator
+        s_main = s_pan = s_crit = cache["s_main"]
+        crit_group = group
 
     # ---- assembly (no communication) -------------------------------------------------------------------
     cols = cache["cols"]
@@ -206,23 +218,19 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
 
     logdet = torch.zeros(1, dtype=torch.float64, device=dev)
     quad = torch.zeros(1, dtype=torch.float64, device=dev)
-    pans, Wks, piece, Rloc = cache["pans"], cache["Wks"], cache["piece"], cache["Rloc"]
+    pans, Wks, blks, piece, Rloc = cache["pans"], cache["Wks"], cache["blks"], cache["piece"], cache["Rloc"]
     ak = torch.zeros(nb, 2, dtype=torch.float64, device=dev)
-    ev_pan = [None, None]
+    ev_W, ev_blk, ev_pan, ev_la, ev_done = {}, {}, {}, {}, {-1: ev_main}
 
-    def apply_panel(k, j, pan, stream_rows):
-        """A_j -= L[rows >= j, k] L[j, k]^T on the local rows (stream_rows: panel rows of the local block rows > k)."""
-        if j not in cols:
-            return
-        f = first_local_row(j)
-        fk = first_local_row(k + 1)
-        m = (len(R) - f) * nb
-        if m <= 0:
-            return
-        ops.gemm(False, True, m, nb, nb, -1.0, stream_rows[(f - fk) * nb:], pan[(j - k - 1) * nb:(j - k) * nb], 1.0, cols[j])
+    def rank_of(i, j):
+        return (i % P) * Q + (j % Q)
+
+    def local_off(j, i):
+        """Row offset of block row i inside cols[j] (i is local, i >= j)."""
+        return ((i - p) // P - first_local_row(j)) * nb
 
     def gather_local_rows(k, pan, out):
-        """out <- panel rows of the local block rows > k, contiguous (strided block slice of the global-order panel)."""
+        """out <- panel-k rows of the local block rows > k, contiguous (strided block slice of the global-order panel)."""
         fk = first_local_row(k + 1)
         n = len(R) - fk
         if n > 0:
@@ -230,25 +238,67 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
             out[:n * nb].view(n, nb, nb).copy_(pan[:(nblk - k - 1) * nb].view(nblk - k - 1, nb, nb)[s0::P])
         return out
 
-    def factor_panel(k, buf):
-        """Runs on s_pan: diagonal block, panel solve and the broadcasts of step k into pans[buf] / Wks[buf]."""
-        kp, kq = k % P, k % Q
-        pan, Wk = pans[buf], Wks[buf]
-        mine = (q == kq) and (k in cols)
+    def apply_panel(k, j, pan, rows, skip_diag):
+        """cols[j] -= L[i, k] L[j, k]^T for the local block rows i >= j (i > j when skip_diag); rows = gather_local_rows(k)."""
+        if j not in cols:
+            return
+        f = first_local_row(j + 1 if skip_diag else j)
+        m = (len(R) - f) * nb
+        if m <= 0:
+            return
+        fk, fj = first_local_row(k + 1), first_local_row(j)
+        ops.gemm(False, True, m, nb, nb, -1.0, rows[(f - fk) * nb:], pan[(j - k - 1) * nb:(j - k) * nb], 1.0, cols[j][(f - fj) * nb:])
+
+    # Who applies panel k to block column j (so that no block is ever updated from two streams at once):
+    #   diagonal block (j, j):  main for k <= j-3, crit for k = j-2 (from pan_k) and k = j-1 (from the early block blk_k)
+    #   rows below it:          main for k <= j-2, pan (look-ahead) for k = j-1
+    def crit_step(k):
+        """Critical path of step k: factor the diagonal block, broadcast its inverse, solve + broadcast the ONE block
+        (k+1, k) and finish the next diagonal block, so that potrf(k+1) never waits for the bulk of panel k."""
+        buf = k % 2
+        Wk, blk = Wks[buf], blks[buf]
+        ops.wait(s_crit, ev_done.get(k - 2))  # W/blk buffers free; main's updates of the blocks touched below are complete
         with _Phase("diag_potrf_inv"):
-            if q == kq and p == kp:
+            if rank == rank_of(k, k):
                 A = cols[k]
                 ops.potrf_inv(A[:nb], Wk)
                 logdet.add_(torch.log(A[:nb].diagonal()).sum())
         with _Phase("bcast_W"):
-            dist.broadcast(Wk, src=kp * Q + kq, group=group)
+            dist.broadcast(Wk, src=rank_of(k, k), group=crit_group)
+        ev_W[k] = ops.record(s_crit)
+        if k + 1 >= nblk:
+            return
+        with _Phase("early_block"):
+            src = rank_of(k + 1, k)
+            if rank == src:
+                ops.wait(s_crit, ev_la.get(k - 1))  # block (k+1, k) carries panel k-1 (look-ahead of the previous step)
+                o = local_off(k, k + 1)
+                ops.gemm(False, True, nb, nb, nb, 1.0, cols[k][o:o + nb], Wk, 0.0, blk)
+                cols[k][o:o + nb].copy_(blk)
+            dist.broadcast(blk, src=src, group=crit_group)
+            ev_blk[k] = ops.record(s_crit)
+            if rank == rank_of(k + 1, k + 1):
+                D = cols[k + 1][:nb]
+                if k >= 1:
+                    ops.wait(s_crit, ev_pan.get(k - 1))
+                    L1 = pans[(k - 1) % 2][nb:2 * nb]  # L[k+1, k-1]
+                    ops.gemm(False, True, nb, nb, nb, -1.0, L1, L1, 1.0, D)
+                ops.gemm(False, True, nb, nb, nb, -1.0, blk, blk, 1.0, D)
+
+    def pan_step(k):
+        """Bulk of step k: rest of the panel solve, the P panel broadcasts, look-ahead update of column k+1."""
         nbelow = nblk - k - 1
         if nbelow == 0:
             return
+        buf = k % 2
+        pan, Wk = pans[buf], Wks[buf]
+        kq = k % Q
+        ops.wait(s_pan, ev_done.get(k - 2))  # rows of column k carry panels <= k-2; pans[buf] is no longer read by main
+        ops.wait(s_pan, ev_blk.get(k))       # W_k and the solved block (k+1, k) are in place
         with _Phase("panel_solve"):
-            if mine:
+            if q == kq and k in cols:
                 A = cols[k]
-                off = nb if p == kp else 0
+                off = (first_local_row(k + 2) - first_local_row(k)) * nb  # skip the diagonal block and block k+1
                 m = A.shape[0] - off
                 if m > 0:
                     tmp = piece[:m]
@@ -261,55 +311,54 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
             cnt = (nblk - 1 - i0) // P + 1
             src = pp * Q + kq
             if rank == src:
-                off = nb if pp == kp else 0
-                buf_t = cols[k][off:off + cnt * nb]
+                o = local_off(k, i0)
+                buf_t = cols[k][o:o + cnt * nb]
             else:
                 buf_t = piece[:cnt * nb]
             with _Phase("bcast_panel"):
                 dist.broadcast(buf_t, src=src, group=group)
                 pan[:nbelow * nb].view(nbelow, nb, nb)[i0 - (k + 1)::P].copy_(buf_t.view(cnt, nb, nb))
+        ev_pan[k] = ops.record(s_pan)
+        ops.wait(s_pan, ev_done.get(k - 1))  # main has finished applying panel k-1 to the same rows of column k+1
+        with _Phase("lookahead_update"):
+            if k + 1 in cols:
+                rows = gather_local_rows(k, pan, piece)  # `piece` is idle between the broadcasts of two steps
+                apply_panel(k, k + 1, pan, rows, skip_diag=True)
+        ev_la[k] = ops.record(s_pan)
 
-    with ops.use(s_pan):
-        ops.wait(s_pan, ev_main)
-        factor_panel(0, 0)
-        ev_pan[0] = ops.record(s_pan)
-
-    for k in range(nblk):
+    def main_step(k):
+        """Forward substitution piece (replicated) and the trailing update of the block columns > k+1."""
+        nbelow = nblk - k - 1
         buf = k % 2
         pan, Wk = pans[buf], Wks[buf]
-        nbelow = nblk - k - 1
-        nxt = k + 1
-        if lookahead and nxt < nblk:
-            with ops.use(s_pan):
-                ops.wait(s_pan, ev_main)  # column k+1 carries every update up to panel k-1; buffer (k+1)%2 is free again
-                with _Phase("lookahead_update"):
-                    if nxt in cols:
-                        rows_pan = gather_local_rows(k, pan, piece)  # `piece` is idle between the broadcasts of two steps
-                        apply_panel(k, nxt, pan, rows_pan)
-                factor_panel(nxt, nxt % 2)
-                ev_pan[nxt % 2] = ops.record(s_pan)
+        ops.wait(s_main, ev_W.get(k))
+        ops.wait(s_main, ev_pan.get(k))
+        with _Phase("forward_subst"):  # a_k = W_kk y_k ; y[k+1:] -= L[k+1:, k] a_k
+            ops.gemm(False, False, nb, 2, nb, 1.0, Wk, y[k * nb:(k + 1) * nb], 0.0, ak)
+            quad.add_((ak[:, 0] * ak[:, 0]).sum())
+            if nbelow:
+                ops.gemm(False, False, nbelow * nb, 2, nb, -1.0, pan, ak, 1.0, y[(k + 1) * nb:])
+        with _Phase("trailing_update"):
+            if nbelow > 1:
+                rows = gather_local_rows(k, pan, Rloc)
+                for j in Cb:
+                    if j >= k + 2:
+                        apply_panel(k, j, pan, rows, skip_diag=(j == k + 2))
+        ev_done[k] = ops.record(s_main)
+
+    with ops.use(s_crit):
+        ops.wait(s_crit, ev_main)
+        crit_step(0)
+    for k in range(nblk):
+        with ops.use(s_pan):
+            pan_step(k)
+        if k + 1 < nblk:
+            with ops.use(s_crit):
+                crit_step(k + 1)
         with ops.use(s_main):
-            ops.wait(s_main, ev_pan[buf])
-            # a_k = W_kk y_k ; y[k+1:] -= L[k+1:, k] a_k   (replicated on every rank)
-            with _Phase("forward_subst"):
-                ops.gemm(False, False, nb, 2, nb, 1.0, Wk, y[k * nb:(k + 1) * nb], 0.0, ak)
-                quad.add_((ak[:, 0] * ak[:, 0]).sum())
-                if nbelow:
-                    ops.gemm(False, False, nbelow * nb, 2, nb, -1.0, pan, ak, 1.0, y[(k + 1) * nb:])
-            with _Phase("trailing_update"):
-                if nbelow:
-                    rows_pan = gather_local_rows(k, pan, Rloc)
-                    for j in Cb:
-                        if j > k and not (lookahead and j == nxt):
-                            apply_panel(k, j, pan, rows_pan)
-            ev_main = ops.record(s_main)
-        if not lookahead and nxt < nblk:
-            with ops.use(s_pan):
-                ops.wait(s_pan, ev_main)
-                factor_panel(nxt, nxt % 2)
-                ev_pan[nxt % 2] = ops.record(s_pan)
+            main_step(k)
     with ops.use(s_main):
-        ops.wait(s_main, ev_pan[(nblk - 1) % 2])
+        ops.wait(s_main, ev_W.get(nblk - 1))
         dist.all_reduce(logdet, group=group)
     ops.finish()
     ld = float(logdet.item()) - (0.5 * npad * math.log(noise) if npad else 0.0)

@@ -20,7 +20,7 @@ class CpuOpsDouble:
         self.torch = torch
         self.device = torch.device("cpu")
 
-    def new_stream(self):
+    def new_stream(self, high_priority=False):
         return None
 
     def use(self, stream):
