@@ -12,8 +12,7 @@ the replicated inputs with the fused covariance kernel (no communication), then 
 with LOOK-AHEAD on three CUDA streams: the CRITICAL stream factors the diagonal block, broadcasts its inverse, solves
 and broadcasts only the single block (k+1, k) and completes the next diagonal block, so potrf(k+1) starts ~0.3 ms after
 potrf(k) ends; the PANEL stream solves and broadcasts the bulk of panel k and updates block column k+1; the MAIN stream
-applies panel k to the rest of the trailing matrix.  Critical and bulk broadcasts use two communicators so that a small
-broadcast never queues behind a 100 MB panel.  NLML = 1/2 |a|^2 + sum log L_ii + N/2 log 2 pi  (GPflow GPR.log_marginal_likelihood,
+applies panel k to the rest of the trailing matrix.  NLML = 1/2 |a|^2 + sum log L_ii + N/2 log 2 pi  (GPflow GPR.log_marginal_likelihood,
 reference call sites mfgpflow/linear.py:206,227).  P = 1 gives the 1-D block-cyclic column layout of round 1.
 
 All device arithmetic goes through libmfgp.so (`GpuOps`); torch supplies buffers, streams and NCCL.  The block
@@ -23,6 +22,7 @@ lives in tests/, the product path has no CPU fallback."""
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 
@@ -46,7 +46,9 @@ class GpuOps:
         self.torch, self._lib, self.h = torch, _lib, handle
         self.L = _lib._lib
         self.device = torch.device("cuda", torch.cuda.current_device())
-        handle.set_async(True)
+
+    def begin(self):
+        self.h.set_async(True)  # library calls only enqueue; finish() collects the status
 
     def _chk(self, rc, what):
         if rc != 0:
@@ -130,7 +132,15 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
                 torch.cuda.synchronize()
                 profile[self.name] = profile.get(self.name, 0.0) + time.perf_counter() - self.t0
 
-    ops = handle_or_ops if hasattr(handle_or_ops, "potrf_inv") else GpuOps(handle_or_ops)
+    if hasattr(handle_or_ops, "potrf_inv"):
+        ops = handle_or_ops
+    else:  # a library handle: keep the GpuOps (and with it the cached streams / workspaces) on the handle
+        ops = getattr(handle_or_ops, "_dist_ops", None)
+        if ops is None:
+            ops = GpuOps(handle_or_ops)
+            handle_or_ops._dist_ops = ops
+    if hasattr(ops, "begin"):
+        ops.begin()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     P, Q = grid if grid is not None else process_grid(world)
     if P * Q != world:
@@ -191,10 +201,16 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
             pass
     if lookahead:
         s_main, s_pan, s_crit = cache["s_main"], cache["s_pan"], cache["s_crit"]
-        if cache.get("crit_group") is None:  # second communicator: critical-path broadcasts never queue behind a panel
-            ranks = dist.get_process_group_ranks(group if group is not None else dist.group.WORLD)
-            cache["crit_group"] = dist.new_group(ranks=ranks)
-        crit_group = cache["crit_group"]
+        # One communicator: NCCL executes its collectives in issue order (W_k, blk_k, panel k, W_k+1, ...), which is also
+        # the dependency order.  A second communicator for the small broadcasts was measured 10x SLOWER on 4 GPUs (two NCCL
+        # kernels of different communicators spin against each other); MFGP_DIST_TWO_COMMS=1 re-enables it for experiments.
+        if os.environ.get("MFGP_DIST_TWO_COMMS") == "1":
+            if cache.get("crit_group") is None:
+                ranks = dist.get_process_group_ranks(group if group is not None else dist.group.WORLD)
+                cache["crit_group"] = dist.new_group(ranks=ranks)
+            crit_group = cache["crit_group"]
+        else:
+            crit_group = group
     else:  # reference schedule: the same steps, one stream, one communicator
         s_main = s_pan = s_crit = cache["s_main"]
         crit_group = group
@@ -346,6 +362,7 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
                         apply_panel(k, j, pan, rows, skip_diag=(j == k + 2))
         ev_done[k] = ops.record(s_main)
 
+    t_issue0 = time.perf_counter()
     with ops.use(s_crit):
         ops.wait(s_crit, ev_main)
         crit_step(0)
@@ -360,6 +377,11 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
     with ops.use(s_main):
         ops.wait(s_main, ev_W.get(nblk - 1))
         dist.all_reduce(logdet, group=group)
+    t_issue1 = time.perf_counter()
     ops.finish()
+    stats = getattr(ops, "stats", None)
+    if isinstance(stats, dict):  # host time to ISSUE the factorisation vs. time until the device has finished it
+        stats["host_issue_s"] = t_issue1 - t_issue0
+        stats["device_done_s"] = time.perf_counter() - t_issue0
     ld = float(logdet.item()) - (0.5 * npad * math.log(noise) if npad else 0.0)
     return 0.5 * float(quad.item()) + ld + 0.5 * N0 * math.log(2.0 * math.pi)
