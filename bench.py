@@ -276,7 +276,7 @@ def run_mine(args):
             "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic restarts on the in-repo HBS2021 arrays", "config": config(R, extra),
             "roofline": {"bound": "tensor", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "gpr_small_kernel",
+                         "frac": achieved / peak, "traffic": None, "kernel": "gpr_small_v4_kernel<7,5>",
                          "peak_source": "measured live: FP64 pipe microbenchmark (DMMA m8n8k4 / DFMA), "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "alg_flops_per_bin": ALG_FLOPS_PER_BIN},
