@@ -234,3 +234,35 @@ def test_batched_not_pd_reports_per_problem_info(h):
     with pytest.raises(NotPositiveDefiniteError):
         h.gpr_batched_nlml_grad(X, Y, th, nz, info=info)
     assert info[0] == 0 and info[2] == 0 and info[1] > 0
+
+
+def test_cov_streaming_kernel_full_size_properties(h):
+    """BASELINE config 5 size (N = 16 384, d = 10, 1/8 HF): the streaming K1 path (prescale + persistent CTAs + bulk-store
+    mirror).  Size-independent properties: K(X,X) is exactly symmetric, equals the rectangular evaluation K(X, X2 = copy)
+    to rounding, has var_L / rho^2 var_L + var_delta on the diagonal, and sampled elements match the oracle to 1e-12."""
+    import torch
+
+    from multi_fidelity_gpflow_b200 import _lib
+
+    ds = onp.synthetic_exact_dataset(16384)
+    X, th = ds["X"], ds["theta"]
+    N, d = X.shape[0], X.shape[1] - 1
+    dev = torch.device("cuda:0")
+    tX, tth = torch.from_numpy(X).to(dev), torch.from_numpy(th).to(dev)
+    K = torch.empty(N, N, dtype=torch.float64, device=dev)
+    assert _lib._lib.mfgp_cov(h._h, _lib._ptr(tX), N, None, N, d, _lib._ptr(tth), _lib._ptr(K), N) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(K, K.T)
+    tX2 = tX.clone()
+    K2 = torch.empty(N, N, dtype=torch.float64, device=dev)
+    assert _lib._lib.mfgp_cov(h._h, _lib._ptr(tX), N, _lib._ptr(tX2), N, d, _lib._ptr(tth), _lib._ptr(K2), N) == 0
+    torch.cuda.synchronize()
+    assert float((K - K2).abs().max()) <= 1e-13 * float(K.abs().max())
+    np.testing.assert_allclose(K.diagonal().cpu().numpy(), onp.mf_K_diag(X, th), rtol=1e-13)
+    rng = np.random.default_rng(0)
+    ii, jj = rng.integers(0, N, 4000), rng.integers(0, N, 4000)
+    ii[:500] = rng.integers(N * 7 // 8, N, 500)  # make sure HF x HF pairs are sampled
+    jj[:500] = rng.integers(N * 7 // 8, N, 500)
+    got = K[torch.from_numpy(ii).to(dev), torch.from_numpy(jj).to(dev)].cpu().numpy()
+    ref = np.array([onp.mf_K(X[i:i + 1], X[j:j + 1], th)[0, 0] for i, j in zip(ii, jj)])
+    np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-12)
