@@ -78,6 +78,20 @@ int mfgp_gpr_batched_nlml_grad(mfgp_handle* h, const double* X, int N, int d, co
                                long ldy, int ycols, int B, const double* theta, const double* noise,
                                double* nlml, double* grad, int* info);
 
+/* Training loop on the device: the Adam branch of MultiFidelityGPModel.optimize (mfgpflow/linear.py:
+ * 190-221: loss = -log_marginal_likelihood, tape.gradient w.r.t. the UNCONSTRAINED variables, Keras Adam, noise fixed) for
+ * B independent per-bin GPs, nsteps steps without a host round trip.  Per step: theta = softplus(u) -> K6 NLML + gradient
+ * -> chain rule (1 - exp(-theta)) -> m, v, u update (ResourceApplyAdam: m += (g-m)(1-beta1), v += (g^2-v)(1-beta2),
+ * u -= lr_t m / (sqrt(v) + eps)).  u, m, v are [B, 2d+3] and updated in place (m = v = 0 to start); lr_t [nsteps] holds
+ * the per-step factor lr(step) sqrt(1-beta2^t)/(1-beta1^t), computed by the host shim so that the float32-rounded
+ * hyper-parameters and the CosineDecay schedule of the reference (quirk Q8) stay in one place.  fix_rho != 0 freezes rho
+ * (use_rho=False, linear.py:51-52).  loss_hist [nsteps, B] (or NULL) receives the NLML evaluated BEFORE each update (the
+ * reference's loss_history); theta_out [B, 2d+3] (or NULL) the constrained values after the last update.
+ * N <= 64 only (the K6 kernel).  Returns >0 if a Cholesky failed at any step (per-problem first failure in info[B]). */
+int mfgp_gpr_batched_adam(mfgp_handle* h, const double* X, int N, int d, const double* Y, long ldy, int ycols, int B,
+                          double* u, double* m, double* v, const double* noise, const double* lr_t, double beta1,
+                          double beta2, double eps, int fix_rho, int nsteps, double* loss_hist, double* theta_out, int* info);
+
 /* ---- K7/K8: sparse variational GP (whitened, shared inducing points) -------------------
  * replaces gpflow SVGP.elbo / prior_kl / predict_f as called at singlebin_svgp.py:83,97 and
  * linear_svgp.py:177,184,188,199 with kernels SeparateIndependent (W == NULL, L == P,

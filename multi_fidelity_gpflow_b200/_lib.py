@@ -48,6 +48,7 @@ def _load():
         "mfgp_gpr_nlml_grad": ([vp, vp, vp, i, i, i, vp, d, vp, vp], i),
         "mfgp_gpr_predict": ([vp, vp, vp, i, i, i, vp, i, vp, d, vp, vp], i),
         "mfgp_gpr_batched_nlml_grad": ([vp, vp, i, i, vp, l, i, i, vp, vp, vp, vp, vp], i),
+        "mfgp_gpr_batched_adam": ([vp, vp, i, i, vp, l, i, i, vp, vp, vp, vp, vp, d, d, d, i, i, vp, vp, vp], i),
         "mfgp_svgp_elbo_grad": ([vp, vp, vp, vp, vp, vp, vp, vp, vp, d, vp, vp, vp, vp, vp, vp, vp, vp], i),
         "mfgp_svgp_predict": ([vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp], i),
         "mfgp_gemm": ([vp, C.c_char, C.c_char, i, i, i, d, vp, l, vp, l, d, vp, l], i),
@@ -66,7 +67,7 @@ _lib = _load()
 EXPORTED_SYMBOLS = [
     "mfgp_version", "mfgp_create", "mfgp_destroy", "mfgp_set_stream", "mfgp_reset_stream", "mfgp_set_async", "mfgp_sync",
     "mfgp_last_error", "mfgp_sm_count", "mfgp_cov", "mfgp_cov_diag", "mfgp_gpr_nlml", "mfgp_gpr_nlml_grad",
-    "mfgp_gpr_predict", "mfgp_gpr_batched_nlml_grad", "mfgp_svgp_elbo_grad", "mfgp_svgp_predict", "mfgp_gemm",
+    "mfgp_gpr_predict", "mfgp_gpr_batched_nlml_grad", "mfgp_gpr_batched_adam", "mfgp_svgp_elbo_grad", "mfgp_svgp_predict", "mfgp_gemm",
     "mfgp_potrf", "mfgp_potrf_inv", "mfgp_fp64_peak",
 ]
 
@@ -220,6 +221,23 @@ class Handle:
         )
         self._check(rc, "mfgp_gpr_batched_nlml_grad")
         return nlml, grad
+
+    def gpr_batched_adam(self, X, Y, u, m, v, noises, lr_t, beta1, beta2, eps=1e-7, fix_rho=False, loss_hist=None,
+                         theta_out=None, info=None):
+        """nsteps = len(lr_t) Adam steps on the device for B = u.shape[0] per-bin GPs; u, m, v [B, 2d+3] are updated in
+        place (host arrays or device tensors).  Returns (loss_hist, theta_out)."""
+        X, Y, noises, lr_t = as_f64(X), as_f64(Y), as_f64(noises), as_f64(lr_t)
+        N, d = X.shape[0], X.shape[1] - 1
+        ycols = ldy = Y.shape[1]
+        B, nsteps = u.shape[0], int(lr_t.shape[0])
+        for a in (u, m, v):
+            if isinstance(a, np.ndarray) and not (a.dtype == np.float64 and a.flags.c_contiguous):
+                raise ValueError("u, m, v must be C-contiguous float64 (they are updated in place)")
+        rc = _lib.mfgp_gpr_batched_adam(self._h, _ptr(X), N, d, _ptr(Y), ldy, ycols, B, _ptr(u), _ptr(m), _ptr(v), _ptr(noises),
+                                        _ptr(lr_t), float(beta1), float(beta2), float(eps), int(bool(fix_rho)), nsteps,
+                                        _ptr(loss_hist), _ptr(theta_out), _ptr(info))
+        self._check(rc, "mfgp_gpr_batched_adam")
+        return loss_hist, theta_out
 
     # -- SVGP ----------------------------------------------------------------------------------
     def svgp_elbo_grad(self, X, Y, Z, thetas, W, q_mu, q_sqrt, lik_var, scale=1.0, kl_mult=1.0, hetero=False,

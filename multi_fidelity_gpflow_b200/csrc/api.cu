@@ -226,6 +226,85 @@ int mfgp_gpr_batched_nlml_grad(mfgp_handle* h, const double* X, int N, int d, co
 }
 
 // ---------------------------------------------------------------------------------------------
+// Device-resident Adam loop for the batched per-bin GPs (reference loop mfgpflow/linear.py:190-221).
+namespace {
+__device__ __forceinline__ double softplus_fwd(double u) {  // gpflow.utilities.positive(): tfp Softplus, lower = 0
+    return u > 0.0 ? u + log1p(exp(-u)) : log1p(exp(u));
+}
+__global__ void adam_softplus_kernel(const double* __restrict__ u, double* __restrict__ theta, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) theta[i] = softplus_fwd(u[i]);
+}
+// One thread per (problem, parameter): chain rule, moment update, step, and theta for the NEXT evaluation.
+__global__ void adam_update_kernel(double* __restrict__ u, double* __restrict__ m, double* __restrict__ v,
+                                   double* __restrict__ theta, const double* __restrict__ grad, const double* __restrict__ nlml,
+                                   const double* __restrict__ lr_t, int step, double b1, double b2, double eps, int fix_rho,
+                                   int np, int B, double* __restrict__ loss_hist, const int* __restrict__ step_info,
+                                   int* __restrict__ first_info) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)B * np) return;
+    const int b = (int)(i / np), q = (int)(i % np);
+    if (q == 0) {
+        if (loss_hist) loss_hist[(long)step * B + b] = nlml[b];
+        if (first_info && step_info[b] && !first_info[b]) first_info[b] = step_info[b];
+    }
+    if (fix_rho && q == 0) return;
+    const double th = theta[i];
+    const double g = grad[(long)b * (np + 1) + q] * (1.0 - exp(-th));  // d theta / d u = sigmoid(u) = 1 - exp(-theta)
+    double mi = m[i], vi = v[i];
+    mi += (g - mi) * (1.0 - b1);
+    vi += (g * g - vi) * (1.0 - b2);
+    const double un = u[i] - lr_t[step] * mi / (sqrt(vi) + eps);
+    m[i] = mi;
+    v[i] = vi;
+    u[i] = un;
+    theta[i] = softplus_fwd(un);
+}
+}  // namespace
+
+int mfgp_gpr_batched_adam(mfgp_handle* h, const double* X, int N, int d, const double* Y, long ldy, int ycols, int B,
+                          double* u, double* m, double* v, const double* noise, const double* lr_t, double beta1,
+                          double beta2, double eps, int fix_rho, int nsteps, double* loss_hist, double* theta_out, int* info) {
+    CHECK_H(h);
+    if (!X || !Y || !u || !m || !v || !noise || !lr_t || N < 1 || B < 0 || d < 1 || ycols < 1 || ldy < ycols || nsteps < 0)
+        return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_gpr_batched_adam: bad argument");
+    if (N > MFGP_SMALL_MAX_N || d > MFGP_SMALL_MAX_D)
+        return mfgp_fail(h, MFGP_ERR_UNSUPPORTED, "mfgp_gpr_batched_adam: N <= 64 and d <= 16 only");
+    cudaSetDevice(h->device);
+    if (B == 0 || nsteps == 0) return 0;
+    const int np = 2 * d + 3;
+    const size_t n = (size_t)B * np;
+    Scope sc(h);
+    const double* dX = sc.in(X, (size_t)N * (d + 1));
+    const double* dY = sc.in(Y, (size_t)N * ldy);
+    const double* dnz = sc.in(noise, B);
+    const double* dlr = sc.in(lr_t, nsteps);
+    double* du = sc.inout(u, n);
+    double* dm = sc.inout(m, n);
+    double* dv = sc.inout(v, n);
+    double* dl = loss_hist ? sc.out(loss_hist, (size_t)nsteps * B) : nullptr;
+    double* dto = theta_out ? sc.out(theta_out, n) : nullptr;
+    int* di = info ? sc.out(info, B, true) : nullptr;
+    double* dth = sc.alloc<double>(n);
+    double* dn = sc.alloc<double>(B);
+    double* dg = sc.alloc<double>((size_t)B * (np + 1));
+    int* dsi = sc.alloc<int>(B);
+    if (!sc.ok) return sc.finish();
+    const int tb = 256;
+    const unsigned gb = (unsigned)((n + tb - 1) / tb);
+    adam_softplus_kernel<<<gb, tb, 0, h->stream>>>(du, dth, (long)n);
+    SmallArgs a{};
+    a.X = dX; a.N = N; a.d = d; a.Y = dY; a.ldy = ldy; a.ycols = ycols; a.B = B;
+    a.theta = dth; a.noise = dnz; a.nlml = dn; a.grad = dg; a.info = dsi; a.d_info = h->d_info;
+    for (int s = 0; s < nsteps; ++s) {
+        if (launch_gpr_small_v4(h->stream, a)) return mfgp_fail(h, MFGP_ERR_CUDA, "gpr_small launch failed");
+        adam_update_kernel<<<gb, tb, 0, h->stream>>>(du, dm, dv, dth, dg, dn, dlr, s, beta1, beta2, eps, fix_rho, np, B, dl, dsi, di);
+    }
+    if (dto) CUDA_TRY(h, cudaMemcpyAsync(dto, dth, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return sc.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
 int mfgp_gemm(mfgp_handle* h, char transa, char transb, int m, int n, int k, double alpha, const double* A, long lda,
               const double* B, long ldb, double beta, double* C, long ldc) {
     CHECK_H(h);

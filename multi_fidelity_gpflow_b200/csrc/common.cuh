@@ -114,6 +114,18 @@ struct Scope {
         host_out = true;
         return d;
     }
+    // in/out buffer: staged to the device now and copied back by finish() when p is host memory
+    template <typename T>
+    T* inout(T* p, size_t count) {
+        if (!p) return nullptr;
+        if (mfgp_is_device_ptr(p)) return p;
+        T* d = alloc<T>(count);
+        if (!d) return nullptr;
+        if (cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) ok = false;
+        outs.push_back({p, d, count * sizeof(T)});
+        host_out = true;
+        return d;
+    }
     // copy results back, synchronise unless (async && no host outputs), collect info
     int finish() {
         if (!ok) return mfgp_fail(h, MFGP_ERR_CUDA, "%s", h->err[0] ? h->err : "allocation / staging failed");
