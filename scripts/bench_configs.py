@@ -66,12 +66,26 @@ def main():
         out[f"{name}_latent_svgp_elbo_grad"] = {"gpu_evals_per_s": 1 / g, "cpu_evals_per_s": 1 / c, "M": M, "L": L, "B": N}
         print(json.dumps({k: v for k, v in out.items() if k.startswith(name)}, indent=1), flush=True)
     # C5: synthetic exact GPR
-    for N in (4096, 8192, 16384):
+    for N in (4096, 8192, 16384, 32768):
         ds = onp.synthetic_exact_dataset(N)
         g = timeit(lambda: h.gpr_nlml_grad(ds["X"], ds["Y"], ds["theta"], ds["noise"]), 2, 1)
         flops = N**3 + 4 * N**2
         out[f"synthetic_exact_gpr_N{N}"] = {"gpu_evals_per_s": 1 / g, "sec": g, "alg_tflops": flops / g / 1e12}
         print(N, out[f"synthetic_exact_gpr_N{N}"], flush=True)
+    # device-resident Adam training of 49 bins x R restarts (MultiBinMFGP)
+    from multi_fidelity_gpflow_b200.multibin import MultiBinMFGP
+
+    ds = onp.load_dataset("hbs")
+    for R, steps in ((1, 200), (64, 200), (4096, 50)):
+        mdl = MultiBinMFGP(ds["X"], ds["Y"], num_restarts=R, seed=0, handle=h)
+        mdl.optimize(max_iters=5, learning_rate=0.01)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mdl.optimize(max_iters=steps, learning_rate=0.01)
+        dt = time.perf_counter() - t0
+        out[f"hbs_device_adam_R{R}"] = {"steps": steps, "sec": dt, "adam_steps_per_s": steps / dt,
+                                        "bin_gp_evals_per_s": steps * R * 49 / dt, "us_per_step": dt / steps * 1e6}
+        print(R, out[f"hbs_device_adam_R{R}"], flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/configs.json", "w"), indent=1)
 
