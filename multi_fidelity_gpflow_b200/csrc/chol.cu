@@ -12,6 +12,8 @@
 // (reference call sites linear.py:206, singlebin_svgp.py:83, linear_svgp.py:184).
 #include "chol.cuh"
 
+#include <cstdlib>
+
 #include "gemm.cuh"
 
 namespace {
@@ -306,10 +308,18 @@ int launch_potrf(cudaStream_t s, const CholArgs& a) {
     const int N = a.N;
     const int nblk = chol_nblk(N);
     const long stride_dinv = (long)nblk * NB * NB;
-    constexpr int OB = 2 * NB;  // outer block: the trailing update is a rank-256 GEMM (two 128-wide panels)
+    // outer block: the trailing update is a rank-OB GEMM (OB / 128 panels of 128 columns); wider = fewer read-modify-write
+    // passes over the trailing matrix and longer DMMA main loops per tile, at the price of more skinny inner updates on
+    // the panel stream.  Measured on B200 (scripts/potrf_once.py): see DESIGN.md section 5.
+    static const int OB = [] {
+        const char* e = getenv("MFGP_POTRF_OB");
+        int v = e ? atoi(e) : 4 * NB;  // 512: N = 16 384 24.6 TFLOP/s (256: 24.0), N = 32 768 28.9 (256: 27.3)
+        if (v < NB) v = NB;
+        return (v / NB) * NB;
+    }();
     // Look-ahead: the latency-bound chain  diag -> panel -> inner update -> diag -> panel  runs on the aux stream and
     // overlaps the FP64-bound trailing update of the previous outer step; the main stream hands over the next
-    // 256 columns early.
+    // OB columns early.
     const bool la = a.aux != nullptr && a.ev != nullptr && N > 2 * OB;
     cudaStream_t sp = la ? a.aux : s;
     if (la) {
@@ -362,15 +372,15 @@ int launch_potrf(cudaStream_t s, const CholArgs& a) {
     int step = 0;
     for (int K0 = 0; K0 < N; K0 += OB, ++step) {
         const int w = N - K0 < OB ? N - K0 : OB;
-        const int nb1 = w < NB ? w : NB, nb2 = w - nb1;
         cudaEvent_t ev_col = la ? a.ev[2 * (step & 1)] : nullptr, ev_panel = la ? a.ev[2 * (step & 1) + 1] : nullptr;
         if (la && step > 0) cudaStreamWaitEvent(sp, ev_col, 0);  // columns [K0, K0+w) fully updated
-        diag(K0, nb1);
-        if (panel(K0, nb1, K0 + nb1)) return -2;
-        if (nb2 > 0) {
-            if (update(sp, K0 + nb1, K0 + nb1, nb2, K0, nb1, 0)) return -2;  // second half of the outer block
-            diag(K0 + nb1, nb2);
-            if (panel(K0 + nb1, nb2, K0 + w)) return -2;
+        // factor the outer block column panel by panel (left-looking inside the block: panel j first receives the
+        // rank-(j*128) update from the panels already finished in this block)
+        for (int j0 = 0; j0 < w; j0 += NB) {
+            const int nbj = w - j0 < NB ? w - j0 : NB;
+            if (j0 > 0 && update(sp, K0 + j0, K0 + j0, nbj, K0, j0, 0)) return -2;
+            diag(K0 + j0, nbj);
+            if (panel(K0 + j0, nbj, K0 + j0 + nbj)) return -2;
         }
         const int rem = N - K0 - w;
         if (rem <= 0) break;
