@@ -122,6 +122,18 @@ int mfgp_svgp_predict(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* Xs
                       const double* Z, const double* theta, const double* W, const double* q_mu,
                       const double* q_sqrt, double* mean, double* var);
 
+/* Training loop on the device for the SVGP models: the optimize() loops of mfgpflow/singlebin_svgp.py:
+ * 64-97 and mfgpflow/linear_svgp.py:153-203 -- full-batch, Keras Adam (+ CosineDecay folded into lr_t, see
+ * mfgp_gpr_batched_adam), loss = -ELBO + (kl_mult - 1) KL -- nsteps steps without a host round trip.
+ * Flat parameter layout (doubles): [theta L*(2d+3)] [Z M*(d+1)] [W P*L, only if has_W] [q_mu M*L] [q_sqrt L*M*M] [lik_var 1].
+ * u holds the UNCONSTRAINED values in that layout (theta = softplus(u), lik_var = 1e-6 + softplus(u), the rest identity;
+ * the strictly upper part of every q_sqrt matrix must be zero and stays zero); u, m, v are updated in place.
+ * mask (n bytes or NULL): 0 freezes an entry (not in trainable_variables).  loss_hist / kl_hist [nsteps] or NULL receive
+ * the loss and KL evaluated BEFORE each update (the reference's loss_history / kl_history). */
+int mfgp_svgp_adam(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* X, const double* Y, int has_W, double* u,
+                   double* m, double* v, const unsigned char* mask, const double* lr_t, double beta1, double beta2,
+                   double eps, int nsteps, double* loss_hist, double* kl_hist);
+
 /* ---- dense fp64 building blocks (exported for tests / bench / comparators) ------------- */
 /* C[m,n] = alpha * op(A) op(B) + beta * C, row-major; transa/transb are 'N' or 'T'.
  * Runs the DMMA (mma.sync m8n8k4 f64) tile kernel. */

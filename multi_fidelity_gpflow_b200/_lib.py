@@ -51,6 +51,7 @@ def _load():
         "mfgp_gpr_batched_adam": ([vp, vp, i, i, vp, l, i, i, vp, vp, vp, vp, vp, d, d, d, i, i, vp, vp, vp], i),
         "mfgp_svgp_elbo_grad": ([vp, vp, vp, vp, vp, vp, vp, vp, vp, d, vp, vp, vp, vp, vp, vp, vp, vp], i),
         "mfgp_svgp_predict": ([vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp], i),
+        "mfgp_svgp_adam": ([vp, vp, vp, vp, i, vp, vp, vp, vp, vp, d, d, d, i, vp, vp], i),
         "mfgp_gemm": ([vp, C.c_char, C.c_char, i, i, i, d, vp, l, vp, l, d, vp, l], i),
         "mfgp_potrf": ([vp, vp, i, l], i),
         "mfgp_potrf_inv": ([vp, vp, i, l, vp, l], i),
@@ -67,7 +68,7 @@ _lib = _load()
 EXPORTED_SYMBOLS = [
     "mfgp_version", "mfgp_create", "mfgp_destroy", "mfgp_set_stream", "mfgp_reset_stream", "mfgp_set_async", "mfgp_sync",
     "mfgp_last_error", "mfgp_sm_count", "mfgp_cov", "mfgp_cov_diag", "mfgp_gpr_nlml", "mfgp_gpr_nlml_grad",
-    "mfgp_gpr_predict", "mfgp_gpr_batched_nlml_grad", "mfgp_gpr_batched_adam", "mfgp_svgp_elbo_grad", "mfgp_svgp_predict", "mfgp_gemm",
+    "mfgp_gpr_predict", "mfgp_gpr_batched_nlml_grad", "mfgp_gpr_batched_adam", "mfgp_svgp_elbo_grad", "mfgp_svgp_predict", "mfgp_svgp_adam", "mfgp_gemm",
     "mfgp_potrf", "mfgp_potrf_inv", "mfgp_fp64_peak",
 ]
 
@@ -221,6 +222,22 @@ class Handle:
         )
         self._check(rc, "mfgp_gpr_batched_nlml_grad")
         return nlml, grad
+
+    def svgp_adam(self, X, Y, L, M, P, has_W, u, m, v, mask, lr_t, beta1, beta2, eps=1e-7, scale=1.0, kl_mult=1.0,
+                  hetero=False, jitter=1e-6):
+        """len(lr_t) full-batch Adam steps on the device; u, m, v (flat layout of include/mfgp.h) are updated in place.
+        Returns (loss_hist, kl_hist)."""
+        X, Y, lr_t = as_f64(X), as_f64(Y), as_f64(lr_t)
+        B, d = X.shape[0], X.shape[1] - 1
+        cfg = SvgpCfg(L, M, P, B, d, int(hetero), float(scale), float(kl_mult), float(jitter))
+        n = int(lr_t.shape[0])
+        loss, kl = np.empty(n), np.empty(n)
+        mk = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        rc = _lib.mfgp_svgp_adam(self._h, C.byref(cfg), _ptr(X), _ptr(Y), int(bool(has_W)), _ptr(u), _ptr(m), _ptr(v),
+                                 None if mk is None else C.c_void_p(mk.ctypes.data), _ptr(lr_t), float(beta1), float(beta2),
+                                 float(eps), n, _ptr(loss), _ptr(kl))
+        self._check(rc, "mfgp_svgp_adam")
+        return loss, kl
 
     def gpr_batched_adam(self, X, Y, u, m, v, noises, lr_t, beta1, beta2, eps=1e-7, fix_rho=False, loss_hist=None,
                          theta_out=None, info=None):

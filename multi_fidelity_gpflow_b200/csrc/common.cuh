@@ -23,6 +23,7 @@ struct mfgp_handle {
     int sm_count = 148;
     int* d_info = nullptr;   // device: first failing pivot (1-based), 0 = ok
     int* h_info = nullptr;   // pinned mirror
+    const double* lik_var_dev = nullptr;  // when set, the SVGP likelihood variance is read from the device (training loop)
     char err[512] = {0};
 };
 

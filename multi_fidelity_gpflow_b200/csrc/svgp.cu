@@ -77,8 +77,10 @@ __global__ void col_reduce_kernel(const double* __restrict__ A, const double* __
 __global__ void mix_ve_kernel(int mode, const double* __restrict__ g_mean, const double* __restrict__ g_var, int L,
                               int B, int P, const double* __restrict__ W, const double* __restrict__ Y, int hetero,
                               double lik_var, double scale, double* __restrict__ fbm, double* __restrict__ fbv,
-                              double* __restrict__ part, double* __restrict__ mean, double* __restrict__ var) {
+                              double* __restrict__ part, double* __restrict__ mean, double* __restrict__ var,
+                              const double* __restrict__ lik_var_dev = nullptr) {
     __shared__ double sh[8];
+    if (lik_var_dev) lik_var = *lik_var_dev;
     const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
     double ve = 0.0, lb = 0.0;
     if (idx < (long)B * P) {
@@ -424,7 +426,7 @@ int mfgp_svgp_elbo_grad(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* 
     double* gth_ws = sc.alloc<double>((size_t)L * (2 * d + 4), true);
     if (!sc.ok) return sc.finish();
     mix_ve_kernel<<<nblk, 256, 0, s>>>(0, f.g_mean, f.g_var, L, B, P, dW, dY, cfg->hetero, lik_var, cfg->scale, fbm, fbv,
-                                       part, nullptr, nullptr);
+                                       part, nullptr, nullptr, h->lik_var_dev);
     kl_kernel<<<L, 256, 0, s>>>(dqm, f.Lq, M, f.ldM, L, klpart);
 
     if (want_grad) {
@@ -570,3 +572,89 @@ int mfgp_svgp_predict(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* Xs
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Device-resident Adam loop for the SVGP models: the optimize() loops of
+// mfgpflow/singlebin_svgp.py:64-97 and mfgpflow/linear_svgp.py:153-203 (full-batch, Adam + CosineDecay, loss =
+// -ELBO + (kl_multiplier - 1) KL) without a host round trip per step.
+namespace {
+__device__ __forceinline__ double sp_fwd(double u) { return u > 0.0 ? u + log1p(exp(-u)) : log1p(exp(u)); }
+// segment boundaries of the flat layout: [0, n_theta) softplus; [n_theta, n - 1) identity; n - 1: 1e-6 + softplus
+__global__ void svgp_constrain_kernel(const double* __restrict__ u, double* __restrict__ c, long n, long n_theta) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = u[i];
+    c[i] = i < n_theta ? sp_fwd(x) : (i == n - 1 ? 1e-6 + sp_fwd(x) : x);
+}
+__global__ void svgp_adam_kernel(double* __restrict__ u, double* __restrict__ m, double* __restrict__ v,
+                                 const double* __restrict__ c, const double* __restrict__ g, const unsigned char* __restrict__ mask,
+                                 long n, long n_theta, const double* __restrict__ lr_t, int step, double b1, double b2, double eps,
+                                 const double* __restrict__ elbo_kl, double kl_mult, double* __restrict__ loss_hist,
+                                 double* __restrict__ kl_hist) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        if (loss_hist) loss_hist[step] = -elbo_kl[0] + (kl_mult - 1.0) * elbo_kl[1];
+        if (kl_hist) kl_hist[step] = elbo_kl[1];
+    }
+    if (i >= n || (mask && !mask[i])) return;
+    double gu = g[i];
+    if (i < n_theta) gu *= 1.0 - exp(-c[i]);                  // d softplus
+    else if (i == n - 1) gu *= 1.0 - exp(-(c[i] - 1e-6));     // lower bound 1e-6 (gpflow Gaussian likelihood)
+    double mi = m[i], vi = v[i];
+    mi += (gu - mi) * (1.0 - b1);
+    vi += (gu * gu - vi) * (1.0 - b2);
+    u[i] -= lr_t[step] * mi / (sqrt(vi) + eps);
+    m[i] = mi;
+    v[i] = vi;
+}
+}  // namespace
+
+extern "C" int mfgp_svgp_adam(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* X, const double* Y, int has_W, double* u,
+                              double* m, double* v, const unsigned char* mask, const double* lr_t, double beta1, double beta2,
+                              double eps, int nsteps, double* loss_hist, double* kl_hist) {
+    if (!h) return MFGP_ERR_ARG;
+    if (!cfg || !X || !Y || !u || !m || !v || !lr_t || nsteps < 0)
+        return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_svgp_adam: NULL argument");
+    const int L = cfg->L, M = cfg->M, P = cfg->P, B = cfg->B, d = cfg->d;
+    if (L < 1 || M < 1 || P < 1 || B < 1 || d < 1 || d > MFGP_MAX_D || (!has_W && L != P))
+        return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_svgp_adam: bad configuration");
+    if (nsteps == 0) return 0;
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    const long n_theta = (long)L * (2 * d + 3), n_Z = (long)M * (d + 1), n_W = has_W ? (long)P * L : 0, n_qm = (long)M * L,
+               n_qs = (long)L * M * M;
+    const long o_Z = n_theta, o_W = o_Z + n_Z, o_qm = o_W + n_W, o_qs = o_qm + n_qm, o_lv = o_qs + n_qs, n = o_lv + 1;
+    const int ycols = cfg->hetero ? 2 * P : P;
+    int rc = 0;
+    {
+        Scope sc(h);
+        const double* dX = sc.in(X, (size_t)B * (d + 1));
+        const double* dY = sc.in(Y, (size_t)B * ycols);
+        const double* dlr = sc.in(lr_t, nsteps);
+        const unsigned char* dmask = mask ? sc.in(mask, (size_t)n) : nullptr;
+        double* du = sc.inout(u, (size_t)n);
+        double* dm = sc.inout(m, (size_t)n);
+        double* dv = sc.inout(v, (size_t)n);
+        double* dl = loss_hist ? sc.out(loss_hist, nsteps) : nullptr;
+        double* dk = kl_hist ? sc.out(kl_hist, nsteps) : nullptr;
+        double* c = sc.alloc<double>((size_t)n);
+        double* g = sc.alloc<double>((size_t)n, true);
+        double* ek = sc.alloc<double>(2);
+        if (!sc.ok) return sc.finish();
+        const int tb = 256;
+        const unsigned gb = (unsigned)((n + tb - 1) / tb);
+        const int was_async = h->async;
+        h->async = 1;  // the nested evaluations only enqueue: all their pointers are device memory
+        h->lik_var_dev = c + o_lv;
+        for (int st = 0; st < nsteps && rc == 0; ++st) {
+            svgp_constrain_kernel<<<gb, tb, 0, s>>>(du, c, n, n_theta);
+            rc = mfgp_svgp_elbo_grad(h, cfg, dX, dY, c + o_Z, c, has_W ? c + o_W : nullptr, c + o_qm, c + o_qs, 0.0, ek, ek + 1,
+                                     g + o_Z, g, has_W ? g + o_W : nullptr, g + o_qm, g + o_qs, g + o_lv);
+            svgp_adam_kernel<<<gb, tb, 0, s>>>(du, dm, dv, c, g, dmask, n, n_theta, dlr, st, beta1, beta2, eps, ek, cfg->kl_mult, dl, dk);
+        }
+        h->lik_var_dev = nullptr;
+        h->async = was_async;
+        if (rc) return rc;
+        return sc.finish();
+    }
+}

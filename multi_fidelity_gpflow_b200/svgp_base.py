@@ -118,6 +118,63 @@ class SVGPBase:
         loss = -r["elbo"] + (kl_multiplier - 1.0) * r["kl"]
         return loss, r["kl"], [np.asarray(by[id(p)], dtype=np.float64).reshape(p.shape) for p in variables]
 
+    # ---- device-resident training loop --------------------------------------------
+    def _flat_parameters(self, d):
+        """(list of (Parameter, flat slice, per-entry source index or None), n): the flat layout of mfgp_svgp_adam."""
+        W = getattr(self.kernel, "W", None)
+        items, o = [], 0
+        for k in self.kernel.kernels:
+            for par, cnt in ((k.rho, 1), (k.kernel_L.lengthscales, d), (k.kernel_L.variance, 1), (k.kernel_delta.lengthscales, d),
+                             (k.kernel_delta.variance, 1)):
+                if int(np.size(par.unconstrained)) != cnt:
+                    raise NotImplementedError("the device loop needs one rho per kernel and ARD lengthscales of shape (d,); "
+                                              "use optimize() (host loop) for shared lengthscales")
+                items.append((par, slice(o, o + cnt)))
+                o += cnt
+        for par in [self.Z] + ([W] if W is not None else []) + [self.q_mu, self.q_sqrt, self.likelihood.variance]:
+            cnt = int(np.size(par.unconstrained))
+            items.append((par, slice(o, o + cnt)))
+            o += cnt
+        return items, o
+
+    def optimize_on_device(self, data, max_iters, initial_lr, kl_multiplier=1.0):
+        """The model's optimize() loop -- full-batch Adam with CosineDecay(initial_lr, max_iters) on the unconstrained
+        trainable variables, loss = -ELBO + (kl_multiplier - 1) KL -- run by mfgp_svgp_adam without a host round trip per
+        step.  Same trajectory as optimize() (tests/test_svgp_device_loop.py); appends to loss_history / kl_history."""
+        import math
+
+        from .optimizers import CosineDecay
+
+        X, Y = data
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        d = X.shape[1] - 1
+        items, n = self._flat_parameters(d)
+        u, mask = np.empty(n), np.zeros(n, dtype=np.uint8)
+        for par, sl in items:
+            vals = np.ravel(par.unconstrained)
+            if par is self.q_sqrt:
+                vals = np.ravel(np.tril(par.unconstrained))
+            u[sl] = vals
+            mask[sl] = 1 if par.trainable else 0
+        steps = int(max_iters)
+        b1, b2 = float(np.float32(0.9)), float(np.float32(0.999))
+        sched = CosineDecay(initial_lr, max_iters)
+        lr_t = np.array([sched(s) * math.sqrt(1.0 - b2 ** (s + 1.0)) / (1.0 - b1 ** (s + 1.0)) for s in range(steps)])
+        m, v = np.zeros(n), np.zeros(n)
+        M, L = self.q_mu.shape
+        W = getattr(self.kernel, "W", None)
+        P = L if W is None else W.shape[0]
+        scale = 1.0 if self.num_data is None else float(self.num_data) / X.shape[0]
+        loss, kl = self.handle.svgp_adam(X, Y, L, M, P, W is not None, u, m, v, mask, lr_t, b1, b2, 1e-7, scale=scale,
+                                         kl_mult=kl_multiplier, hetero=self.likelihood.heteroscedastic)
+        for par, sl in items:
+            par.unconstrained = u[sl].reshape(np.shape(par.unconstrained)).copy()
+        self.loss_history = list(self.loss_history) + list(loss)
+        if hasattr(self, "kl_history"):
+            self.kl_history = list(self.kl_history) + list(kl)
+        return self
+
     def predict_f(self, Xnew, full_cov=False, full_output_cov=False):
         if full_cov or full_output_cov:
             raise NotImplementedError("the reference only calls predict_f(Xnew) (marginal variances)")

@@ -1,0 +1,74 @@
+"""GPU tests: the device-resident SVGP training loop (mfgp_svgp_adam) follows the same trajectory as the models' host
+optimize() loops (mirrors of mfgpflow/singlebin_svgp.py:64-97 and mfgpflow/linear_svgp.py:153-203)."""
+import copy
+
+import numpy as np
+import pytest
+
+from oracle import mfgp_oracle as onp
+
+pytestmark = pytest.mark.gpu
+
+
+def _kernels(d):
+    from multi_fidelity_gpflow_b200.kernels import SquaredExponential
+
+    return SquaredExponential(lengthscales=np.ones(d)), SquaredExponential(lengthscales=np.ones(d))
+
+
+def _params(model):
+    out = [model.q_mu.numpy(), np.tril(model.q_sqrt.numpy()), model.Z.numpy(), np.ravel(model.likelihood.variance.numpy())]
+    W = getattr(model.kernel, "W", None)
+    if W is not None:
+        out.append(W.numpy())
+    out.append(np.stack([k.theta(5) for k in model.kernel.kernels]))
+    return out
+
+
+def test_singlebin_svgp_device_loop_equals_host_loop():
+    from multi_fidelity_gpflow_b200.singlebin_svgp import SingleBinSVGP
+
+    ds = onp.load_dataset("hbs")
+    X, Y = ds["X"], np.ascontiguousarray(ds["Y"][:, :6])
+    kL, kD = _kernels(5)
+    a = SingleBinSVGP(X, Y, kL, kD, 6, ds["Z_kmeans50"])
+    b = copy.deepcopy(a)
+    a.optimize((X, Y), max_iters=12, initial_lr=0.01, verbose=False)
+    b.optimize_on_device((X, Y), max_iters=12, initial_lr=0.01)
+    np.testing.assert_allclose(b.loss_history, a.loss_history, rtol=1e-10)
+    for pa, pb in zip(_params(a), _params(b)):
+        np.testing.assert_allclose(pb, pa, rtol=1e-8, atol=1e-10)
+    # fidelity column of Z never moves (quirk Q5: its gradient is exactly zero)
+    assert np.array_equal(b.Z.numpy()[:, -1], ds["Z_kmeans50"][:, -1]) or np.allclose(b.Z.numpy()[:, -1], a.Z.numpy()[:, -1], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("klm", [1.0, 2.5])
+def test_latent_svgp_device_loop_equals_host_loop(klm):
+    from multi_fidelity_gpflow_b200.linear_svgp import LatentMFCoregionalizationSVGP
+
+    ds = onp.load_dataset("hbs")
+    X, Y = ds["X"], ds["Y"]
+    kL, kD = _kernels(5)
+    a = LatentMFCoregionalizationSVGP(X, Y, kL, kD, num_latents=4, num_inducing=20, num_outputs=49)
+    b = copy.deepcopy(a)
+    a.optimize((X, Y), max_iters=10, initial_lr=0.005, kl_multiplier=klm, verbose=False)
+    b.optimize_on_device((X, Y), max_iters=10, initial_lr=0.005, kl_multiplier=klm)
+    np.testing.assert_allclose(b.loss_history, a.loss_history, rtol=1e-10)
+    np.testing.assert_allclose(b.kl_history, a.kl_history, rtol=1e-10, atol=1e-12)
+    for pa, pb in zip(_params(a), _params(b)):
+        np.testing.assert_allclose(pb, pa, rtol=1e-8, atol=1e-10)
+
+
+def test_frozen_parameters_stay_put():
+    from multi_fidelity_gpflow_b200.base import set_trainable
+    from multi_fidelity_gpflow_b200.linear_svgp import LatentMFCoregionalizationSVGP
+
+    ds = onp.load_dataset("hbs")
+    X, Y = ds["X"], ds["Y"]
+    kL, kD = _kernels(5)
+    mdl = LatentMFCoregionalizationSVGP(X, Y, kL, kD, num_latents=3, num_inducing=16, num_outputs=49, w_type="fixed_independent")
+    set_trainable(mdl.likelihood.variance, False)
+    W0, lv0 = mdl.kernel.W.numpy().copy(), mdl.likelihood.variance.numpy().copy()
+    mdl.optimize_on_device((X, Y), max_iters=5, initial_lr=0.01)
+    assert np.array_equal(mdl.kernel.W.numpy(), W0) and np.array_equal(mdl.likelihood.variance.numpy(), lv0)
+    assert mdl.loss_history[-1] < mdl.loss_history[0]
