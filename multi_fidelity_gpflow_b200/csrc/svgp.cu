@@ -18,6 +18,8 @@
 // Every O(M^2 B) / O(M^3) product is a DMMA GEMM (gemm.cu); the rest are streaming kernels.
 #include "svgp.cuh"
 
+#include <cstdlib>
+
 #include "chol.cuh"
 #include "cov.cuh"
 #include "gemm.cuh"
@@ -588,10 +590,11 @@ __global__ void svgp_constrain_kernel(const double* __restrict__ u, double* __re
 }
 __global__ void svgp_adam_kernel(double* __restrict__ u, double* __restrict__ m, double* __restrict__ v,
                                  const double* __restrict__ c, const double* __restrict__ g, const unsigned char* __restrict__ mask,
-                                 long n, long n_theta, const double* __restrict__ lr_t, int step, double b1, double b2, double eps,
-                                 const double* __restrict__ elbo_kl, double kl_mult, double* __restrict__ loss_hist,
-                                 double* __restrict__ kl_hist) {
+                                 long n, long n_theta, const double* __restrict__ lr_t, const int* __restrict__ step_ptr, double b1,
+                                 double b2, double eps, const double* __restrict__ elbo_kl, double kl_mult,
+                                 double* __restrict__ loss_hist, double* __restrict__ kl_hist) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int step = *step_ptr;  // device-side step counter: the same captured graph is replayed for every step
     if (i == 0) {
         if (loss_hist) loss_hist[step] = -elbo_kl[0] + (kl_mult - 1.0) * elbo_kl[1];
         if (kl_hist) kl_hist[step] = elbo_kl[1];
@@ -607,6 +610,7 @@ __global__ void svgp_adam_kernel(double* __restrict__ u, double* __restrict__ m,
     m[i] = mi;
     v[i] = vi;
 }
+__global__ void svgp_step_inc_kernel(int* step) { ++*step; }
 }  // namespace
 
 extern "C" int mfgp_svgp_adam(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* X, const double* Y, int has_W, double* u,
@@ -646,12 +650,41 @@ extern "C" int mfgp_svgp_adam(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const do
         const int was_async = h->async;
         h->async = 1;  // the nested evaluations only enqueue: all their pointers are device memory
         h->lik_var_dev = c + o_lv;
-        for (int st = 0; st < nsteps && rc == 0; ++st) {
+        int* dstep = sc.alloc<int>(1, true);
+        if (!sc.ok) return sc.finish();
+        auto one_step = [&]() -> int {
             svgp_constrain_kernel<<<gb, tb, 0, s>>>(du, c, n, n_theta);
-            rc = mfgp_svgp_elbo_grad(h, cfg, dX, dY, c + o_Z, c, has_W ? c + o_W : nullptr, c + o_qm, c + o_qs, 0.0, ek, ek + 1,
-                                     g + o_Z, g, has_W ? g + o_W : nullptr, g + o_qm, g + o_qs, g + o_lv);
-            svgp_adam_kernel<<<gb, tb, 0, s>>>(du, dm, dv, c, g, dmask, n, n_theta, dlr, st, beta1, beta2, eps, ek, cfg->kl_mult, dl, dk);
+            int r = mfgp_svgp_elbo_grad(h, cfg, dX, dY, c + o_Z, c, has_W ? c + o_W : nullptr, c + o_qm, c + o_qs, 0.0, ek, ek + 1,
+                                        g + o_Z, g, has_W ? g + o_W : nullptr, g + o_qm, g + o_qs, g + o_lv);
+            svgp_adam_kernel<<<gb, tb, 0, s>>>(du, dm, dv, c, g, dmask, n, n_theta, dlr, dstep, beta1, beta2, eps, ek, cfg->kl_mult, dl, dk);
+            svgp_step_inc_kernel<<<1, 1, 0, s>>>(dstep);
+            return r;
+        };
+        // Step 0 runs eagerly (first-call attribute settings, pool growth).  The remaining steps replay ONE captured CUDA
+        // graph of a whole step (~60 kernels for the small models, where launch latency dominates); if anything in the
+        // step is not capturable the loop falls back to eager launches.
+        rc = one_step();
+        int done = 1;
+        static const bool use_graph = [] { const char* e = getenv("MFGP_SVGP_GRAPH"); return !(e && e[0] == '0'); }();
+        if (rc == 0 && nsteps > 2 && use_graph) {
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+            if (ok) {
+                const int r = one_step();
+                ok = (cudaStreamEndCapture(s, &graph) == cudaSuccess) && r == 0 && graph != nullptr;
+            }
+            if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+            if (ok) {
+                for (; done < nsteps && ok; ++done) ok = cudaGraphLaunch(exec, s) == cudaSuccess;
+                if (!ok) rc = mfgp_fail(h, MFGP_ERR_CUDA, "mfgp_svgp_adam: graph launch failed");
+            } else {
+                cudaGetLastError();  // capture not possible: clear the error, run eagerly
+            }
+            if (exec) cudaGraphExecDestroy(exec);
+            if (graph) cudaGraphDestroy(graph);
         }
+        for (; done < nsteps && rc == 0; ++done) rc = one_step();
         h->lik_var_dev = nullptr;
         h->async = was_async;
         if (rc) return rc;
