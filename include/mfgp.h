@@ -54,6 +54,13 @@ int mfgp_cov(mfgp_handle* h, const double* X, int N, const double* X2, int N2, i
              const double* theta, double* K, long ldk);
 int mfgp_cov_diag(mfgp_handle* h, const double* X, int N, int d, const double* theta, double* out);
 
+/* K5: out[q] = scale * sum_ij G_ij dK_ij/dtheta_q (q < 2d+3) with K = K(X, X; theta) and dK recomputed on the fly (never
+ * stored); out[2d+3] = scale * sum_i G_ii (derivative of the noise term).  G [N, ldg] is symmetric and only its LOWER triangle
+ * is read (off-diagonal entries count twice).  This is the contraction of tape.gradient through K (linear.py:207) exposed for
+ * callers that build G = alpha alpha^T - K^-1 themselves (the distributed exact-GP gradient, dist_chol.py). */
+int mfgp_cov_grad(mfgp_handle* h, const double* X, int N, int d, const double* theta, const double* G, long ldg, double scale,
+                  double* out /* [2d+4] */);
+
 /* ---- K2..K5: exact multi-fidelity GPR -------------------------------------------------
  * replaces gpflow GPR.log_marginal_likelihood as called at linear.py:206,227 (model built
  * at linear.py:148-156: zero mean, Gaussian noise `noise`, ONE kernel/Cholesky shared by

@@ -44,6 +44,7 @@ def _load():
         "mfgp_sm_count": ([vp], i),
         "mfgp_cov": ([vp, vp, i, vp, i, i, vp, vp, l], i),
         "mfgp_cov_diag": ([vp, vp, i, i, vp, vp], i),
+        "mfgp_cov_grad": ([vp, vp, i, i, vp, vp, l, d, vp], i),
         "mfgp_gpr_nlml": ([vp, vp, vp, i, i, i, vp, d, vp], i),
         "mfgp_gpr_nlml_grad": ([vp, vp, vp, i, i, i, vp, d, vp, vp], i),
         "mfgp_gpr_predict": ([vp, vp, vp, i, i, i, vp, i, vp, d, vp, vp], i),
@@ -67,7 +68,7 @@ def _load():
 _lib = _load()
 EXPORTED_SYMBOLS = [
     "mfgp_version", "mfgp_create", "mfgp_destroy", "mfgp_set_stream", "mfgp_reset_stream", "mfgp_set_async", "mfgp_sync",
-    "mfgp_last_error", "mfgp_sm_count", "mfgp_cov", "mfgp_cov_diag", "mfgp_gpr_nlml", "mfgp_gpr_nlml_grad",
+    "mfgp_last_error", "mfgp_sm_count", "mfgp_cov", "mfgp_cov_diag", "mfgp_cov_grad", "mfgp_gpr_nlml", "mfgp_gpr_nlml_grad",
     "mfgp_gpr_predict", "mfgp_gpr_batched_nlml_grad", "mfgp_gpr_batched_adam", "mfgp_svgp_elbo_grad", "mfgp_svgp_predict", "mfgp_svgp_adam", "mfgp_gemm",
     "mfgp_potrf", "mfgp_potrf_inv", "mfgp_fp64_peak",
 ]

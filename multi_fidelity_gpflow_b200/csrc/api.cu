@@ -226,6 +226,35 @@ int mfgp_gpr_batched_nlml_grad(mfgp_handle* h, const double* X, int N, int d, co
 }
 
 // ---------------------------------------------------------------------------------------------
+int mfgp_cov_grad(mfgp_handle* h, const double* X, int N, int d, const double* theta, const double* G, long ldg, double scale,
+                  double* out) {
+    CHECK_H(h);
+    if (!X || !theta || !G || !out || N < 1 || d < 1 || d > MFGP_MAX_D || ldg < N)
+        return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_cov_grad: bad argument");
+    cudaSetDevice(h->device);
+    Scope sc(h);
+    const double* dX = sc.in(X, (size_t)N * (d + 1));
+    const double* dth = sc.in(theta, 2 * d + 3);
+    const double* dG = sc.in(G, (size_t)N * ldg);
+    double* dout = sc.out(out, 2 * d + 4);
+    if (!sc.ok) return sc.finish();
+    CovGradArgs cg{};
+    cg.Xa = dX; cg.Na = N; cg.Xb = dX; cg.Nb = N; cg.d = d;
+    cg.theta = dth; cg.theta_stride = 2 * d + 3;
+    cg.G = dG; cg.ldg = ldg; cg.strideG = 0;
+    cg.sym_lower = 1;
+    cg.out = dout; cg.out_stride = 2 * d + 4;
+    cg.out_scale = scale;
+    cg.accumulate = 0;
+    cg.rowgrad = nullptr;
+    cg.batch = 1;
+    cg.partial = sc.alloc<double>((size_t)cov_grad_partial_count(cg));
+    if (!sc.ok) return sc.finish();
+    if (launch_cov_grad(h->stream, cg)) return mfgp_fail(h, MFGP_ERR_CUDA, "cov_grad launch failed");
+    return sc.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Device-resident Adam loop for the batched per-bin GPs (reference loop mfgpflow/linear.py:190-221).
 namespace {
 __device__ __forceinline__ double softplus_fwd(double u) {  // gpflow.utilities.positive(): tfp Softplus, lower = 0

@@ -97,6 +97,12 @@ class GpuOps:
         self._chk(self.L.mfgp_cov(self.h._h, ptr(Xa), Xa.shape[0], ptr(Xb), Xb.shape[0], Xa.shape[1] - 1, ptr(theta), ptr(out),
                                   out.stride(0)), "cov")
 
+    def cov_grad(self, X, theta, G, scale, out):
+        """out[2d+4] <- scale * sum_ij G_ij dK_ij/dtheta (lower triangle of G, off-diagonal twice), last entry trace(G)."""
+        ptr = self._lib._ptr
+        self._chk(self.L.mfgp_cov_grad(self.h._h, ptr(X), X.shape[0], X.shape[1] - 1, ptr(theta), ptr(G), G.stride(0),
+                                       float(scale), ptr(out)), "cov_grad")
+
     def potrf_inv(self, A, W):
         ptr = self._lib._ptr
         self._chk(self.L.mfgp_potrf_inv(self.h._h, ptr(A), A.shape[0], A.stride(0), ptr(W), W.stride(0)), "potrf_inv")
@@ -107,8 +113,18 @@ class GpuOps:
                                    A.stride(0), ptr(B), B.stride(0), float(beta), ptr(C), C.stride(0)), "gemm")
 
 
-def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None, grid=None, lookahead=True, profile=None):
-    """Every rank passes the same host X [N, d+1], Y [N, 1], theta [2d+3], noise.  Returns the NLML (same on all ranks).
+def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None, grid=None, lookahead=True, profile=None,
+                         want_grad=False):
+    """Every rank passes the same host X [N, d+1], Y [N, 1], theta [2d+3], noise.  Returns the NLML (same on all ranks);
+    with want_grad=True returns (nlml, grad[2d+4]) with grad = d nlml / d [theta, noise] (constrained space), the analogue
+    of tape.gradient at linear.py:207.
+
+    Gradient, designed for 180 GB of HBM per GPU rather than for minimal memory: every panel is
+    already broadcast to every rank by the factorisation, so each rank simply KEEPS the factor (N^2/2 doubles) and the
+    diagonal-block inverses.  Then nothing else needs communication: rank r builds the block ROWS k = r (mod world) of
+    W = L^-1 by block back-substitution (row k = e_k^T L^-1 is independent of the other rows), accumulates its share
+    sum_k W_k^T W_k of K^-1, contracts it with dK/dtheta recomputed on the fly (K5), and ONE all-reduce of 2d+4 numbers
+    finishes  d nlml/d theta = -1/2 tr((alpha alpha^T - K^-1) dK/dtheta).  Flops per rank: 2/3 N^3 / world.
 
     `handle_or_ops`: a `_lib.Handle` (product path) or an object with GpuOps' interface (CPU schedule tests).
     `profile`: optional dict; when given every phase is bracketed by a device synchronize and its wall time is
@@ -199,6 +215,12 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
             ops._dist_chol_ws = cache
         except AttributeError:
             pass
+    if want_grad and "Lcols" not in cache:
+        cache["Lcols"] = [torch.empty(max(nblk - k - 1, 1) * nb, nb, dtype=torch.float64, device=dev) for k in range(nblk)]
+        cache["Wd"] = [torch.empty(nb, nb, dtype=torch.float64, device=dev) for _ in range(nblk)]
+        cache["Kinv"] = torch.empty(N, N, dtype=torch.float64, device=dev)
+        cache["Xrow"] = torch.empty(nb, N, dtype=torch.float64, device=dev)
+        cache["tmpb"] = torch.empty(nb, nb, dtype=torch.float64, device=dev)
     if lookahead:
         s_main, s_pan, s_crit = cache["s_main"], cache["s_pan"], cache["s_crit"]
         # One communicator: NCCL executes its collectives in issue order (W_k, blk_k, panel k, W_k+1, ...), which is also
@@ -236,6 +258,7 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
     quad = torch.zeros(1, dtype=torch.float64, device=dev)
     pans, Wks, blks, piece, Rloc = cache["pans"], cache["Wks"], cache["blks"], cache["piece"], cache["Rloc"]
     ak = torch.zeros(nb, 2, dtype=torch.float64, device=dev)
+    a_all = torch.zeros(N, 2, dtype=torch.float64, device=dev) if want_grad else None
     ev_W, ev_blk, ev_pan, ev_la, ev_done = {}, {}, {}, {}, {-1: ev_main}
 
     def rank_of(i, j):
@@ -352,6 +375,11 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
         with _Phase("forward_subst"):  # a_k = W_kk y_k ; y[k+1:] -= L[k+1:, k] a_k
             ops.gemm(False, False, nb, 2, nb, 1.0, Wk, y[k * nb:(k + 1) * nb], 0.0, ak)
             quad.add_((ak[:, 0] * ak[:, 0]).sum())
+            if want_grad:  # keep the factor: panel k, inv(L_kk) and a_k (every rank has them anyway)
+                a_all[k * nb:(k + 1) * nb].copy_(ak)
+                cache["Wd"][k].copy_(Wk)
+                if nbelow:
+                    cache["Lcols"][k][:nbelow * nb].copy_(pan[:nbelow * nb])
             if nbelow:
                 ops.gemm(False, False, nbelow * nb, 2, nb, -1.0, pan, ak, 1.0, y[(k + 1) * nb:])
         with _Phase("trailing_update"):
@@ -377,6 +405,34 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
     with ops.use(s_main):
         ops.wait(s_main, ev_W.get(nblk - 1))
         dist.all_reduce(logdet, group=group)
+    gout = None
+    if want_grad:
+        with ops.use(s_main), _Phase("gradient"):
+            Lcols, Wd, Kinv, Xrow, tmpb = cache["Lcols"], cache["Wd"], cache["Kinv"], cache["Xrow"], cache["tmpb"]
+            # alpha = L^-T a by block back-substitution (replicated: O(N^2))
+            alpha = torch.zeros(N, 2, dtype=torch.float64, device=dev)
+            tvec = torch.empty(nb, 2, dtype=torch.float64, device=dev)
+            for k in range(nblk - 1, -1, -1):
+                nbelow = nblk - k - 1
+                tvec.copy_(a_all[k * nb:(k + 1) * nb])
+                if nbelow:
+                    ops.gemm(True, False, nb, 2, nbelow * nb, -1.0, Lcols[k], alpha[(k + 1) * nb:], 1.0, tvec)
+                ops.gemm(True, False, nb, 2, nb, 1.0, Wd[k], tvec, 0.0, alpha[k * nb:(k + 1) * nb])
+            # this rank's share of K^-1 = sum_k W_k^T W_k over its block rows k of W = L^-1
+            Kinv.zero_()
+            for k in range(rank, nblk, world):
+                Xrow[:, k * nb:(k + 1) * nb].copy_(Wd[k])
+                for j in range(k - 1, -1, -1):  # W_kj = -(sum_{i=j+1..k} W_ki L_ij) inv(L_jj)
+                    ops.gemm(False, False, nb, nb, (k - j) * nb, 1.0, Xrow[:, (j + 1) * nb:], Lcols[j], 0.0, tmpb)
+                    ops.gemm(False, False, nb, nb, nb, -1.0, tmpb, Wd[j], 0.0, Xrow[:, j * nb:])
+                for c in range(k + 1):  # lower block columns of W_k^T W_k
+                    ops.gemm(True, False, (k + 1 - c) * nb, nb, nb, 1.0, Xrow[:, c * nb:], Xrow[:, c * nb:], 1.0,
+                             Kinv[c * nb:, c * nb:])
+            if rank == 0:  # G = alpha alpha^T - K^-1: the rank-1 term once
+                ops.gemm(False, True, N, N, 2, -1.0, alpha, alpha, 1.0, Kinv)
+            gout = torch.zeros(2 * d + 4, dtype=torch.float64, device=dev)
+            ops.cov_grad(Xd, thd, Kinv, 0.5, gout)  # +1/2 sum (K^-1 - alpha alpha^T) dK = -1/2 sum G dK
+            dist.all_reduce(gout, group=group)
     t_issue1 = time.perf_counter()
     ops.finish()
     stats = getattr(ops, "stats", None)
@@ -384,4 +440,9 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
         stats["host_issue_s"] = t_issue1 - t_issue0
         stats["device_done_s"] = time.perf_counter() - t_issue0
     ld = float(logdet.item()) - (0.5 * npad * math.log(noise) if npad else 0.0)
-    return 0.5 * float(quad.item()) + ld + 0.5 * N0 * math.log(2.0 * math.pi)
+    nlml = 0.5 * float(quad.item()) + ld + 0.5 * N0 * math.log(2.0 * math.pi)
+    if not want_grad:
+        return nlml
+    grad = gout.cpu().numpy().copy()
+    grad[2 * d + 3] -= 0.5 * npad / noise  # the padding rows' log(noise)/2 terms
+    return nlml, grad

@@ -16,6 +16,7 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 nbd = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 grid = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 and sys.argv[3].isdigit() else None
 la = "nolookahead" not in sys.argv
+wg = "grad" in sys.argv
 ds = onp.synthetic_exact_dataset(N)
 res = {}
 for rep in range(3):
@@ -24,12 +25,14 @@ for rep in range(3):
     gops = globals().setdefault("gops", None) or GpuOps(h)
     globals()["gops"] = gops
     gops.stats = {}
-    v = distributed_gpr_nlml(gops, ds["X"], ds["Y"], ds["theta"], ds["noise"], nbd=nbd, grid=grid, lookahead=la)
+    v = distributed_gpr_nlml(gops, ds["X"], ds["Y"], ds["theta"], ds["noise"], nbd=nbd, grid=grid, lookahead=la, want_grad=wg)
+    if wg:
+        v, gvec = v
     torch.cuda.synchronize(); dist.barrier()
     dt = time.perf_counter() - t0
     if rank == 0:
         print(f"world={world} N={N} nbd={nbd} rep {rep}: {dt*1e3:.1f} ms  {N**3/3/dt/1e12:.2f} TFLOP/s (potrf flops)  nlml={v:.6f}  host-issue {gops.stats.get('host_issue_s', 0)*1e3:.1f} ms", flush=True)
-        res = {"world": world, "grid": list(grid) if grid else "auto", "lookahead": la, "N": N, "nbd": nbd, "sec": dt, "potrf_tflops": N**3 / 3 / dt / 1e12, "nlml": v}
+        res = {"with_gradient": wg, "alg_tflops_nlml_grad": (N**3 + 4 * N**2) / dt / 1e12 if wg else None, "world": world, "grid": list(grid) if grid else "auto", "lookahead": la, "N": N, "nbd": nbd, "sec": dt, "potrf_tflops": N**3 / 3 / dt / 1e12, "nlml": v}
 if "profile" in sys.argv:
     prof = {}
     distributed_gpr_nlml(h, ds["X"], ds["Y"], ds["theta"], ds["noise"], nbd=nbd, grid=grid, lookahead=la, profile=prof)
@@ -43,5 +46,5 @@ if rank == 0:
         res["single_gpu_nlml"] = single; res["single_gpu_sec"] = dt1
         print("single-GPU nlml", single, f"{dt1*1e3:.1f} ms", "rel diff", abs(single - res["nlml"]) / abs(single))
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(res, open(f"gpurun_out/dist_chol2d_w{world}_N{N}_nb{nbd}" + ("" if la else "_nola") + ".json", "w"))
+    json.dump(res, open(f"gpurun_out/dist_chol2d_w{world}_N{N}_nb{nbd}" + ("" if la else "_nola") + ("_grad" if wg else "") + ".json", "w"))
 dist.destroy_process_group()

@@ -40,6 +40,18 @@ class CpuOpsDouble:
 
         out.copy_(self.torch.from_numpy(onp.mf_K(Xa.numpy(), Xb.numpy(), theta.numpy())))
 
+    def cov_grad(self, X, theta, G, scale, out):
+        """scale * sum_ij Gs_ij dK_ij/dtheta with Gs = symmetric completion of the lower triangle of G; last entry trace."""
+        from oracle import mfgp_oracle_torch as otc
+
+        torch = self.torch
+        Gs = torch.tril(G) + torch.tril(G, -1).T
+        th = theta.clone().requires_grad_(True)
+        K = otc.mf_K(X, X, th)
+        (Gs * K).sum().backward()
+        out[:-1] = scale * th.grad
+        out[-1] = scale * torch.trace(Gs)
+
     def potrf_inv(self, A, W):
         L = self.torch.linalg.cholesky(A)
         A.copy_(L)
@@ -67,6 +79,10 @@ def _worker(rank, world, port, grid, q):
         ds = onp.synthetic_exact_dataset(N, d=3)
         out[(N, nb, la)] = distributed_gpr_nlml(CpuOpsDouble(), ds["X"], ds["Y"], ds["theta"], ds["noise"], nbd=nb, grid=grid,
                                                 lookahead=la)
+    for N, nb in ((96, 16), (150, 32)):  # value + gradient (ragged N pads the last block)
+        ds = onp.synthetic_exact_dataset(N, d=3)
+        v, g = distributed_gpr_nlml(CpuOpsDouble(), ds["X"], ds["Y"], ds["theta"], ds["noise"], nbd=nb, grid=grid, want_grad=True)
+        out[("grad", N, nb)] = (v, g.tolist())
     if rank == 0:
         q.put(out)
     dist.destroy_process_group()
@@ -91,7 +107,18 @@ def test_block_cyclic_schedule_matches_oracle(world, grid):
     out = q.get(timeout=300)
     for p in procs:
         p.join(60)
-    for (N, nb, la), v in out.items():
+    from oracle import mfgp_oracle_torch as otc
+
+    for key, v in out.items():
+        if key[0] == "grad":
+            _, N, nb = key
+            ds = onp.synthetic_exact_dataset(N, d=3)
+            lml, gth, gnz = otc.gpr_lml_value_and_grad(ds["X"], ds["Y"], ds["theta"], ds["noise"])
+            ref = -np.concatenate([gth, [gnz]])
+            assert abs(v[0] + lml) < 1e-9 * abs(lml)
+            np.testing.assert_allclose(np.array(v[1]), ref, rtol=1e-7, atol=1e-7 * np.abs(ref).max())
+            continue
+        N, nb, la = key
         ds = onp.synthetic_exact_dataset(N, d=3)
         ref = -onp.gpr_lml(ds["X"], ds["Y"], ds["theta"], ds["noise"])
         assert abs(v - ref) < 1e-9 * abs(ref), (N, nb, la, v, ref)

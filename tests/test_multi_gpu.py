@@ -81,11 +81,14 @@ res = {}
 for N, nbd in ((1500, 256), (2048, 512)):
     ds = onp.synthetic_exact_dataset(N)
     v = distributed_gpr_nlml(h, ds["X"], ds["Y"], ds["theta"], ds["noise"], nbd=nbd)
+    v2, g2 = distributed_gpr_nlml(h, ds["X"], ds["Y"], ds["theta"], ds["noise"], nbd=nbd, want_grad=True)
     if rank == 0:
         h.set_stream(None)
         single = h.gpr_nlml(ds["X"], ds["Y"], ds["theta"], ds["noise"])
+        _, gs = h.gpr_nlml_grad(ds["X"], ds["Y"], ds["theta"], ds["noise"])
         ref = -onp.gpr_lml(ds["X"], ds["Y"], ds["theta"], ds["noise"])
-        res[N] = [v, single, ref]
+        gerr = float(np.max(np.abs(g2 - gs)) / np.max(np.abs(gs)))
+        res[N] = [v, single, ref, v2, gerr]
 if rank == 0:
     print("RESULT " + json.dumps(res))
 dist.destroy_process_group()
@@ -105,6 +108,8 @@ def test_two_gpu_distributed_cholesky_nlml(tmp_path):
                           "127.0.0.1", "--master-port", "29632", str(script)], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-3000:]
     r = json.loads([l for l in res.stdout.splitlines() if l.startswith("RESULT ")][0][7:])
-    for N, (v, single, ref) in r.items():
+    for N, (v, single, ref, v2, gerr) in r.items():
         assert abs(v - ref) < 1e-9 * abs(ref), (N, v, ref)
         assert abs(v - single) < 1e-9 * abs(single)
+        assert abs(v2 - v) < 1e-12 * abs(v)  # value identical with and without the gradient phase
+        assert gerr < 1e-7, (N, gerr)        # distributed gradient == single-GPU analytic gradient (1e-7 relative)
