@@ -54,6 +54,15 @@ class GpuOps:
         if rc != 0:
             raise self._lib.MFGPError(f"{what}: rc={rc}: {self.L.mfgp_last_error(self.h._h).decode()}")
 
+    @staticmethod
+    def _vptr(t):
+        """Address of a row-major VIEW (unit column stride; the row stride is passed as the leading dimension)."""
+        import ctypes
+
+        if t.dim() == 2 and t.stride(1) != 1:
+            raise ValueError("matrix views must have unit column stride")
+        return ctypes.c_void_p(t.data_ptr())
+
     # -- streams ---------------------------------------------------------------------------------------
     def new_stream(self, high_priority=False):
         # the panel stream is high priority: its small GEMMs / potrf must not queue behind the trailing update's CTAs
@@ -93,22 +102,22 @@ class GpuOps:
 
     # -- block arithmetic -------------------------------------------------------------------------------
     def cov(self, Xa, Xb, theta, out):
-        ptr = self._lib._ptr
+        ptr = self._vptr
         self._chk(self.L.mfgp_cov(self.h._h, ptr(Xa), Xa.shape[0], ptr(Xb), Xb.shape[0], Xa.shape[1] - 1, ptr(theta), ptr(out),
                                   out.stride(0)), "cov")
 
     def cov_grad(self, X, theta, G, scale, out):
         """out[2d+4] <- scale * sum_ij G_ij dK_ij/dtheta (lower triangle of G, off-diagonal twice), last entry trace(G)."""
-        ptr = self._lib._ptr
+        ptr = self._vptr
         self._chk(self.L.mfgp_cov_grad(self.h._h, ptr(X), X.shape[0], X.shape[1] - 1, ptr(theta), ptr(G), G.stride(0),
                                        float(scale), ptr(out)), "cov_grad")
 
     def potrf_inv(self, A, W):
-        ptr = self._lib._ptr
+        ptr = self._vptr
         self._chk(self.L.mfgp_potrf_inv(self.h._h, ptr(A), A.shape[0], A.stride(0), ptr(W), W.stride(0)), "potrf_inv")
 
     def gemm(self, ta, tb, m, n, k, alpha, A, B, beta, C):
-        ptr = self._lib._ptr
+        ptr = self._vptr
         self._chk(self.L.mfgp_gemm(self.h._h, b"T" if ta else b"N", b"T" if tb else b"N", m, n, k, float(alpha), ptr(A),
                                    A.stride(0), ptr(B), B.stride(0), float(beta), ptr(C), C.stride(0)), "gemm")
 
