@@ -295,6 +295,14 @@ class Handle:
         return mean, var
 
     # -- building blocks -------------------------------------------------------------------------
+    def cov_grad(self, X, theta, G, scale=1.0):
+        """scale * sum_ij G_ij dK_ij/dtheta (lower triangle of the symmetric G, off-diagonal twice) and, last, scale * trace(G)."""
+        X, theta, G = as_f64(X), as_f64(theta), as_f64(G)
+        N, d = X.shape[0], X.shape[1] - 1
+        out = np.empty(2 * d + 4)
+        self._check(_lib.mfgp_cov_grad(self._h, _ptr(X), N, d, _ptr(theta), _ptr(G), G.shape[1], float(scale), _ptr(out)), "mfgp_cov_grad")
+        return out
+
     def gemm(self, ta, tb, A, B, alpha=1.0, beta=0.0, C_in=None):
         A, B = as_f64(A), as_f64(B)
         m = A.shape[1] if ta else A.shape[0]

@@ -266,3 +266,23 @@ def test_cov_streaming_kernel_full_size_properties(h):
     got = K[torch.from_numpy(ii).to(dev), torch.from_numpy(jj).to(dev)].cpu().numpy()
     ref = np.array([onp.mf_K(X[i:i + 1], X[j:j + 1], th)[0, 0] for i, j in zip(ii, jj)])
     np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("N,d", [(53, 5), (130, 3), (700, 10)])
+def test_cov_grad_contraction_vs_autograd(h, N, d):
+    """mfgp_cov_grad: sum_ij G_ij dK_ij/dtheta for a symmetric G given by its lower triangle (the backward pass of K)."""
+    import torch
+
+    rng = np.random.default_rng(N)
+    X = rand_X(rng, N, d, 0.3)
+    th = rand_theta(rng, d)
+    A = rng.standard_normal((N, N))
+    G = A + A.T
+    Glow = np.tril(G) + np.triu(rng.standard_normal((N, N)), 1)  # garbage above the diagonal must be ignored
+    Glow = np.ascontiguousarray(np.pad(Glow, ((0, 0), (0, N % 2))))  # even leading dimension
+    got = h.cov_grad(X, th, Glow, scale=-0.5)
+    tht = torch.tensor(th, requires_grad=True)
+    K = otc.mf_K(torch.from_numpy(X), torch.from_numpy(X), tht)
+    (torch.from_numpy(G) * K).sum().backward()
+    ref = -0.5 * np.concatenate([tht.grad.numpy(), [np.trace(G)]])
+    np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
