@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <vector>
 
 #include "chol.cuh"
 #include "common.cuh"
@@ -31,6 +32,7 @@ int mfgp_create(int device, mfgp_handle** out) {
     h->sm_count = prop.multiProcessorCount;
     cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     for (auto& e : h->ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     h->stream = h->own_stream;
     cudaMalloc(&h->d_info, sizeof(int));
@@ -55,6 +57,7 @@ int mfgp_destroy(mfgp_handle* h) {
     for (auto& e : h->ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->own_stream);
     cudaStreamDestroy(h->aux_stream);
+    cudaStreamDestroy(h->copy_stream);
     cudaFree(h->d_info);
     cudaFreeHost(h->h_info);
     delete h;
@@ -182,6 +185,60 @@ int mfgp_gpr_predict(mfgp_handle* h, const double* X, const double* Y, int N, in
     return sc.finish();
 }
 
+// Large batches with HOST theta / results: the call is pipelined in chunks -- hyper-parameters of chunk c+1 travel to the
+// device (H2D engine, aux stream) and results of chunk c-1 travel back (D2H engine, copy stream) while chunk c is being
+// evaluated, so the end-to-end rate through the C-ABI approaches the device rate instead of (H2D + kernel + D2H) in series.
+static int batched_small_pipelined(mfgp_handle* h, const double* X, int N, int d, const double* Y, long ldy, int ycols, int B,
+                                   const double* theta, const double* noise, double* nlml, double* grad, int* info) {
+    const int np = 2 * d + 3;
+    Scope sc(h);
+    cudaStream_t s = h->stream, sin = h->aux_stream, sout = h->copy_stream;
+    const double* dX = sc.in(X, (size_t)N * (d + 1));
+    const double* dY = sc.in(Y, (size_t)N * ldy);
+    double* dth = sc.alloc<double>((size_t)B * np);
+    double* dnz = sc.alloc<double>(B);
+    double* dn = sc.alloc<double>(B);
+    double* dg = grad ? sc.alloc<double>((size_t)B * (np + 1)) : nullptr;
+    int* di = info ? sc.alloc<int>(B, true) : nullptr;
+    if (!sc.ok) return sc.finish();
+    const long wave = (long)h->sm_count * 12;  // one resident wave of warps
+    long chunk = ((B / 8 + wave - 1) / wave) * wave;
+    if (chunk < 4 * wave) chunk = 4 * wave;
+    const int nch = (int)((B + chunk - 1) / chunk);
+    std::vector<cudaEvent_t> ev(2 * nch + 2);
+    for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventRecord(ev[2 * nch], s);  // buffers exist (stream-ordered allocation) and X, Y are staged
+    cudaStreamWaitEvent(sin, ev[2 * nch], 0);
+    cudaStreamWaitEvent(sout, ev[2 * nch], 0);
+    for (int c = 0; c < nch; ++c) {
+        const long b0 = (long)c * chunk, nb = (B - b0) < chunk ? (B - b0) : chunk;
+        cudaMemcpyAsync(dth + b0 * np, theta + b0 * np, (size_t)nb * np * 8, cudaMemcpyHostToDevice, sin);
+        cudaMemcpyAsync(dnz + b0, noise + b0, (size_t)nb * 8, cudaMemcpyHostToDevice, sin);
+        cudaEventRecord(ev[c], sin);
+    }
+    int rc = 0;
+    for (int c = 0; c < nch && rc == 0; ++c) {
+        const long b0 = (long)c * chunk, nb = (B - b0) < chunk ? (B - b0) : chunk;
+        cudaStreamWaitEvent(s, ev[c], 0);
+        SmallArgs a{};
+        a.X = dX; a.N = N; a.d = d; a.Y = dY; a.ldy = ldy; a.ycols = ycols; a.B = (int)nb; a.prob0 = (int)(b0 % ycols);
+        a.theta = dth + b0 * np; a.noise = dnz + b0; a.nlml = dn + b0; a.grad = dg ? dg + b0 * (np + 1) : nullptr;
+        a.info = di ? di + b0 : nullptr; a.d_info = h->d_info;
+        if (launch_gpr_small_v4(s, a)) rc = mfgp_fail(h, MFGP_ERR_CUDA, "gpr_small launch failed");
+        cudaEventRecord(ev[nch + c], s);
+        cudaStreamWaitEvent(sout, ev[nch + c], 0);
+        cudaMemcpyAsync(nlml + b0, dn + b0, (size_t)nb * 8, cudaMemcpyDeviceToHost, sout);
+        if (dg) cudaMemcpyAsync(grad + b0 * (np + 1), dg + b0 * (np + 1), (size_t)nb * (np + 1) * 8, cudaMemcpyDeviceToHost, sout);
+        if (di) cudaMemcpyAsync(info + b0, di + b0, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, sout);
+    }
+    cudaEventRecord(ev[2 * nch + 1], sout);
+    cudaStreamWaitEvent(s, ev[2 * nch + 1], 0);  // the handle's stream owns the result (and the frees) again
+    sc.host_out = true;                          // host outputs were written: finish() must synchronise
+    const int fin = sc.finish();
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc ? rc : fin;
+}
+
 int mfgp_gpr_batched_nlml_grad(mfgp_handle* h, const double* X, int N, int d, const double* Y, long ldy, int ycols,
                                int B, const double* theta, const double* noise, double* nlml, double* grad, int* info) {
     CHECK_H(h);
@@ -189,6 +246,14 @@ int mfgp_gpr_batched_nlml_grad(mfgp_handle* h, const double* X, int N, int d, co
         return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_gpr_batched_nlml_grad: bad argument");
     cudaSetDevice(h->device);
     if (B == 0) return 0;
+    {
+        static const int which = [] { const char* e = getenv("MFGP_SMALL_KERNEL"); return e ? atoi(e) : 4; }();
+        static const bool pipe = [] { const char* e = getenv("MFGP_BATCH_PIPELINE"); return !(e && e[0] == '0'); }();
+        const bool host_io = !mfgp_is_device_ptr(theta) && !mfgp_is_device_ptr(noise) && !mfgp_is_device_ptr(nlml) &&
+                             (!grad || !mfgp_is_device_ptr(grad)) && (!info || !mfgp_is_device_ptr(info));
+        if (pipe && which == 4 && host_io && N <= MFGP_SMALL_MAX_N && d <= MFGP_SMALL_MAX_D && B >= 16L * h->sm_count * 12)
+            return batched_small_pipelined(h, X, N, d, Y, ldy, ycols, B, theta, noise, nlml, grad, info);
+    }
     Scope sc(h);
     const double* dX = sc.in(X, (size_t)N * (d + 1));
     const double* dY = sc.in(Y, (size_t)N * ldy);

@@ -17,7 +17,8 @@ struct mfgp_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
-    cudaStream_t aux_stream = nullptr;  // look-ahead stream for the panel chain
+    cudaStream_t aux_stream = nullptr;  // look-ahead stream for the panel chain; H2D stream of the pipelined batched call
+    cudaStream_t copy_stream = nullptr; // D2H stream of the pipelined batched call
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int async = 0;
     int sm_count = 148;

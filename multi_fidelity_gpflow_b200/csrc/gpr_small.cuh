@@ -19,6 +19,7 @@ struct SmallArgs {
     int* info;            // [B] or nullptr
     int* d_info;          // handle-wide first failure
     int NP;               // filled by the launcher
+    int prob0;            // v4: index of this launch's first problem in the caller's batch (selects the Y column)
     double* scratch;      // v4: K^L of every problem in flight (L2-resident), filled by the launcher
 };
 int launch_gpr_small(cudaStream_t s, const SmallArgs& a);      // v1: one CTA per problem (DFMA)

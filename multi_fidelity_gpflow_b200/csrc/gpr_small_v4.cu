@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(MAX_WPC * 32, 1) gpr_small_v4_kernel(SmallArgs
                     nL = fma(x, x, nL);
                 }
                 *reinterpret_cast<double2*>(m.hs + 2 * r) = make_double2(fma(-0.5, nL, hlv), live ? (hf ? rho : 1.0) : 0.0);
-                m.yv[r] = (r < N) ? p.Y[(size_t)r * p.ldy + prob % p.ycols] : 0.0;
+                m.yv[r] = (r < N) ? p.Y[(size_t)r * p.ldy + (prob + p.prob0) % p.ycols] : 0.0;
             }
             const unsigned hm = __ballot_sync(0xffffffffu, hf);
             if (hf) m.hidx[nH + __popc(hm & ((1u << lane) - 1u))] = (unsigned char)r;

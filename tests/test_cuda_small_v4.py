@@ -119,3 +119,29 @@ def test_full_bench_batch_properties(h):
     vals, grads = otc.gpr_batched_value_and_grad(X, Y[:, :5], base[:5], nz[:5])
     np.testing.assert_allclose(v[7, :5], -vals, rtol=1e-9)
     np.testing.assert_allclose(g[7, :5], -grads, rtol=1e-7, atol=1e-7 * np.abs(grads).max())
+
+
+def test_pipelined_host_call_equals_device_call(h):
+    """B >= 16 waves with host buffers takes the chunked H2D / compute / D2H pipeline: same bits as the one-launch
+    device-buffer call, including the Y column of every chunk's first problem and per-problem info."""
+    import torch
+
+    ds = onp.load_dataset("hbs")
+    X, Y = ds["X"], ds["Y"]
+    B = 16 * 148 * 12 + 12345  # ragged last chunk
+    rng = np.random.default_rng(9)
+    th = np.tile(onp.default_theta(5), (B, 1)) * np.exp(0.25 * rng.standard_normal((B, 13)))
+    nz = np.full(B, 1e-3)
+    info = np.zeros(B, dtype=np.int32)
+    v_h, g_h = h.gpr_batched_nlml_grad(X, Y, th, nz, info=info)
+    dev = torch.device("cuda:0")
+    tv = torch.empty(B, dtype=torch.float64, device=dev)
+    tg = torch.empty(B, 14, dtype=torch.float64, device=dev)
+    h.gpr_batched_nlml_grad(torch.from_numpy(X).to(dev), torch.from_numpy(np.ascontiguousarray(Y)).to(dev),
+                            torch.from_numpy(th).to(dev), torch.from_numpy(nz).to(dev), nlml=tv, grad=tg)
+    torch.cuda.synchronize()
+    assert np.array_equal(v_h, tv.cpu().numpy()) and np.array_equal(g_h, tg.cpu().numpy())
+    assert not info.any()
+    pick = np.array([0, 1, 7103, 7104, B - 1])
+    vals, grads = otc.gpr_batched_value_and_grad(X, Y[:, pick % 49], th[pick], nz[pick])
+    np.testing.assert_allclose(v_h[pick], -vals, rtol=1e-9)
