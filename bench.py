@@ -284,6 +284,15 @@ def run_mine(args):
             "e2e": {"value": world * R * e2e_steps / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": args.steps, "clocks": clocks,
         }
+        # FP64-pipe occupancy model behind the algorithmic fraction (instruction counts from profiles/r01_ncu_gpr_small_v4_final.csv):
+        # per 53-point problem 518 useful DMMA (16 sub-partition cycles each) + 4 242 scalar FP64 warp-instructions (2 each);
+        # the algorithmic N^3 + 4 N^2 flops are ~1/3 of that work, so `frac` cannot exceed ~0.30 at N = 53.
+        if clocks.get("sm_mhz"):
+            cyc = kernel_sec * clocks["sm_mhz"] * 1e6 * h.sm_count() / nprob
+            full = (518 * 16 + 4242 * 2) / 4.0
+            line["roofline"]["pipe_model"] = {"sm_cycles_per_bin_measured": cyc, "sm_cycles_per_bin_fp64_pipe_only": full,
+                                              "fp64_pipe_busy_est": full / cyc,
+                                              "frac_upper_bound_at_N53": ALG_FLOPS_PER_BIN / 2.0 / 64.0 / full}
         tr = os.path.join(ROOT, "profiles", "traffic_gpr_small.json")
         if os.path.exists(tr):
             try:
