@@ -31,7 +31,14 @@ int mfgp_create(int device, mfgp_handle** out) {
     cudaGetDeviceProperties(&prop, device);
     h->sm_count = prop.multiProcessorCount;
     cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+    {
+        // the panel chain of potrf runs on the aux stream next to the trailing update's thousands of CTAs: highest priority,
+        // so that its few CTAs are scheduled first (MFGP_AUX_PRIORITY=0 restores the default for A/B timing)
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const char* e = getenv("MFGP_AUX_PRIORITY");
+        cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, (e && e[0] == '0') ? lo : hi);
+    }
     cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     for (auto& e : h->ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     h->stream = h->own_stream;
