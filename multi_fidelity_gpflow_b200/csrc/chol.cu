@@ -311,12 +311,14 @@ int launch_potrf(cudaStream_t s, const CholArgs& a) {
     // outer block: the trailing update is a rank-OB GEMM (OB / 128 panels of 128 columns); wider = fewer read-modify-write
     // passes over the trailing matrix and longer DMMA main loops per tile, at the price of more skinny inner updates on
     // the panel stream.  Measured on B200 (scripts/potrf_once.py): see DESIGN.md section 5.
-    static const int OB = [] {
+    static const int OB_env = [] {
         const char* e = getenv("MFGP_POTRF_OB");
-        int v = e ? atoi(e) : 4 * NB;  // 512: N = 16 384 24.6 TFLOP/s (256: 24.0), N = 32 768 28.9 (256: 27.3)
-        if (v < NB) v = NB;
-        return (v / NB) * NB;
+        int v = e ? atoi(e) : 0;
+        return v < NB ? 0 : (v / NB) * NB;
     }();
+    // measured (highest-priority panel stream): N = 8192: 256 -> 18.1, 512 -> 17.1 TFLOP/s; N = 16 384: 256 -> 26.4, 512 -> 26.8;
+    // N = 32 768: 512 -> 29.8
+    const int OB = OB_env ? OB_env : (N <= 12288 ? 2 * NB : 4 * NB);
     // Look-ahead: the latency-bound chain  diag -> panel -> inner update -> diag -> panel  runs on the aux stream and
     // overlaps the FP64-bound trailing update of the previous outer step; the main stream hands over the next
     // OB columns early.
