@@ -10,13 +10,11 @@ lr(step) * sqrt(1 - beta2^t) / (1 - beta1^t).  No CPU fallback: every number com
 """
 from __future__ import annotations
 
-import math
-
 import numpy as np
 
 from . import _lib
 from .base import positive
-from .optimizers import CosineDecay
+from .optimizers import adam_step_factors
 
 
 class MultiBinMFGP:
@@ -63,14 +61,8 @@ class MultiBinMFGP:
 
     # ---- training ------------------------------------------------------------------------------------
     def optimize(self, max_iters=1000, learning_rate=0.01, use_cosine_decay=False, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
-        b1, b2 = float(np.float32(beta_1)), float(np.float32(beta_2))
-        sched = CosineDecay(learning_rate, max_iters) if use_cosine_decay else None
-        lr_t = np.empty(max_iters)
-        for s in range(max_iters):
-            step = self.iterations + s
-            lr = sched(step) if sched else float(np.float32(learning_rate))
-            t = float(step + 1)
-            lr_t[s] = lr * math.sqrt(1.0 - b2**t) / (1.0 - b1**t)
+        lr_t, b1, b2 = adam_step_factors(learning_rate, max_iters, first_step=self.iterations,
+                                         cosine_decay_steps=max_iters if use_cosine_decay else None, beta_1=beta_1, beta_2=beta_2)
         B = self.R * self.P
         hist = np.empty((max_iters, B))
         info = np.zeros(B, dtype=np.int32)

@@ -24,6 +24,22 @@ class CosineDecay:
         return float(np.float32(self.lr0 * dec))
 
 
+def adam_step_factors(learning_rate, num_steps, first_step=0, cosine_decay_steps=None, beta_1=0.9, beta_2=0.999):
+    """Per-step factors lr(step) * sqrt(1 - beta2^t) / (1 - beta1^t), t = step + 1, that the device-resident loops
+    (mfgp_gpr_batched_adam, mfgp_svgp_adam) consume: Keras Adam with float32-stored hyper-parameters (quirk Q8) and the
+    optional CosineDecay(learning_rate, cosine_decay_steps) schedule, evaluated exactly like `Adam.apply_gradients` below.
+    Returns (factors [num_steps], beta1, beta2) with the float32-rounded betas."""
+    b1, b2 = float(np.float32(beta_1)), float(np.float32(beta_2))
+    sched = CosineDecay(learning_rate, cosine_decay_steps) if cosine_decay_steps else None
+    out = np.empty(int(num_steps))
+    for s in range(int(num_steps)):
+        step = first_step + s
+        lr = sched(step) if sched else float(np.float32(learning_rate))
+        t = float(step + 1)
+        out[s] = lr * math.sqrt(1.0 - b2**t) / (1.0 - b1**t)
+    return out, b1, b2
+
+
 class Adam:
     """Keras-2.10 Adam (ResourceApplyAdam): float32-stored lr/beta hypers cast to float64, eps=1e-7,
     zero gradient => zero update."""

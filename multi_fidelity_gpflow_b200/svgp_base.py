@@ -141,9 +141,7 @@ class SVGPBase:
         """The model's optimize() loop -- full-batch Adam with CosineDecay(initial_lr, max_iters) on the unconstrained
         trainable variables, loss = -ELBO + (kl_multiplier - 1) KL -- run by mfgp_svgp_adam without a host round trip per
         step.  Same trajectory as optimize() (tests/test_svgp_device_loop.py); appends to loss_history / kl_history."""
-        import math
-
-        from .optimizers import CosineDecay
+        from .optimizers import adam_step_factors
 
         X, Y = data
         X = np.ascontiguousarray(X, dtype=np.float64)
@@ -157,10 +155,7 @@ class SVGPBase:
                 vals = np.ravel(np.tril(par.unconstrained))
             u[sl] = vals
             mask[sl] = 1 if par.trainable else 0
-        steps = int(max_iters)
-        b1, b2 = float(np.float32(0.9)), float(np.float32(0.999))
-        sched = CosineDecay(initial_lr, max_iters)
-        lr_t = np.array([sched(s) * math.sqrt(1.0 - b2 ** (s + 1.0)) / (1.0 - b1 ** (s + 1.0)) for s in range(steps)])
+        lr_t, b1, b2 = adam_step_factors(initial_lr, int(max_iters), cosine_decay_steps=int(max_iters))
         m, v = np.zeros(n), np.zeros(n)
         M, L = self.q_mu.shape
         W = getattr(self.kernel, "W", None)

@@ -174,3 +174,50 @@ def test_two_rank_gloo_sharding_matches_single_process():
     for k in ("g_Z", "g_thetas", "g_q_mu", "g_q_sqrt", "g_W"):
         np.testing.assert_allclose(out[k], ref[k], rtol=1e-10, atol=1e-12 * np.abs(ref[k]).max())
     assert abs(out["g_lik_var"] - ref["g_lik_var"]) < 1e-10 * abs(ref["g_lik_var"])
+
+
+def test_adam_step_factors_match_tf_adam_emulation():
+    """The per-step factors handed to the device-resident loops reproduce the oracle's TF-Adam (fp32 hypers, CosineDecay)."""
+    from multi_fidelity_gpflow_b200.optimizers import adam_step_factors
+
+    for lr, decay in ((0.01, None), (0.005, 40), (0.1, 7)):
+        f, b1, b2 = adam_step_factors(lr, 25, cosine_decay_steps=decay)
+        ref = onp.TFAdam(lr=lr, cosine_decay_steps=decay)
+        assert b1 == ref.b1 and b2 == ref.b2
+        u = np.array([0.3, -1.2])
+        m, v = np.zeros(2), np.zeros(2)
+        ur = u.copy()
+        rng = np.random.default_rng(0)
+        for s in range(25):
+            g = rng.standard_normal(2)
+            ref.step([ur], [g])
+            m += (g - m) * (1.0 - b1)
+            v += (g * g - v) * (1.0 - b2)
+            u -= f[s] * m / (np.sqrt(v) + 1e-7)
+            np.testing.assert_allclose(u, ur, rtol=1e-14)
+    # resuming: factors of steps 10.. equal the tail of the full schedule (no decay; a decay restarts like the reference)
+    full, _, _ = adam_step_factors(0.01, 30)
+    tail, _, _ = adam_step_factors(0.01, 20, first_step=10)
+    np.testing.assert_array_equal(full[10:], tail)
+
+
+def test_svgp_flat_parameter_layout_matches_the_c_abi():
+    """mfgp_svgp_adam's flat layout [theta | Z | W | q_mu | q_sqrt | lik_var]: sizes, order, freeze mask source."""
+    from multi_fidelity_gpflow_b200.kernels import SquaredExponential
+    from multi_fidelity_gpflow_b200.linear_svgp import LatentMFCoregionalizationSVGP
+
+    ds = onp.load_dataset("hbs")
+    X, Y = ds["X"], ds["Y"]
+    d, L, M, P = 5, 3, 12, 49
+    mdl = LatentMFCoregionalizationSVGP(X, Y, SquaredExponential(lengthscales=np.ones(d)), SquaredExponential(lengthscales=np.ones(d)),
+                                        num_latents=L, num_inducing=M, num_outputs=P)
+    items, n = mdl._flat_parameters(d)
+    assert n == L * (2 * d + 3) + M * (d + 1) + P * L + M * L + L * M * M + 1
+    sizes = [sl.stop - sl.start for _, sl in items]
+    assert sizes[:5] == [1, d, 1, d, 1] and sizes[-5:] == [M * (d + 1), P * L, M * L, L * M * M, 1]
+    assert [sl.start for _, sl in items] == list(np.cumsum([0] + sizes[:-1]))
+    assert items[-1][0] is mdl.likelihood.variance and items[-2][0] is mdl.q_sqrt
+    shared = LatentMFCoregionalizationSVGP(X, Y, SquaredExponential(), SquaredExponential(), num_latents=L, num_inducing=M,
+                                           num_outputs=P)
+    with pytest.raises(NotImplementedError):
+        shared._flat_parameters(d)  # one shared lengthscale: the device loop refuses instead of silently training d copies
