@@ -224,13 +224,12 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
             ops._dist_chol_ws = cache
         except AttributeError:
             pass
-    GR = 4  # block rows of L^-1 built together in the gradient phase
     if want_grad and "Lcols" not in cache:
         cache["Lcols"] = [torch.empty(max(nblk - k - 1, 1) * nb, nb, dtype=torch.float64, device=dev) for k in range(nblk)]
         cache["Wd"] = [torch.empty(nb, nb, dtype=torch.float64, device=dev) for _ in range(nblk)]
         cache["Kinv"] = torch.empty(N, N, dtype=torch.float64, device=dev)
-        cache["Xrow"] = torch.empty(GR * nb, N, dtype=torch.float64, device=dev)
-        cache["tmpb"] = torch.empty(GR * nb, nb, dtype=torch.float64, device=dev)
+        cache["Xrow"] = torch.empty(nb, N, dtype=torch.float64, device=dev)
+        cache["tmpb"] = torch.empty(nb, nb, dtype=torch.float64, device=dev)
     if lookahead:
         s_main, s_pan, s_crit = cache["s_main"], cache["s_pan"], cache["s_crit"]
         # One communicator: NCCL executes its collectives in issue order (W_k, blk_k, panel k, W_k+1, ...), which is also
@@ -428,26 +427,15 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
                 if nbelow:
                     ops.gemm(True, False, nb, 2, nbelow * nb, -1.0, Lcols[k], alpha[(k + 1) * nb:], 1.0, tvec)
                 ops.gemm(True, False, nb, 2, nb, 1.0, Wd[k], tvec, 0.0, alpha[k * nb:(k + 1) * nb])
-            # this rank's share of K^-1 = sum_k W_k^T W_k over its block rows k of W = L^-1.  GROUPS of up to `GR` owned rows
-            # are built together (stacked into one tall matrix, zero beyond each row's diagonal block): the back-substitution
-            # GEMMs get M = GR * nb instead of nb (a 1024 x 1024 output fills < 1 wave of the 148 SMs) and the W^T W
-            # accumulation gets K = GR * nb.
+            # this rank's share of K^-1 = sum_k W_k^T W_k over its block rows k of W = L^-1
             Kinv.zero_()
-            mine = list(range(rank, nblk, world))
-            for g0 in range(0, len(mine), GR):
-                rows = mine[g0:g0 + GR]
-                ng, kmax = len(rows), rows[-1]
-                Xg = Xrow[:ng * nb]
-                Xg[:, :(kmax + 1) * nb].zero_()
-                for gi, k in enumerate(rows):
-                    Xg[gi * nb:(gi + 1) * nb, k * nb:(k + 1) * nb].copy_(Wd[k])
-                for j in range(kmax - 1, -1, -1):  # W_kj = -(sum_{i=j+1..k} W_ki L_ij) inv(L_jj) for every row k > j of the group
-                    a0 = next(gi for gi, k in enumerate(rows) if k > j)
-                    m_act = (ng - a0) * nb
-                    ops.gemm(False, False, m_act, nb, (kmax - j) * nb, 1.0, Xg[a0 * nb:, (j + 1) * nb:], Lcols[j], 0.0, tmpb)
-                    ops.gemm(False, False, m_act, nb, nb, -1.0, tmpb, Wd[j], 0.0, Xg[a0 * nb:, j * nb:])
-                for c in range(kmax + 1):  # lower block columns of sum_k W_k^T W_k
-                    ops.gemm(True, False, (kmax + 1 - c) * nb, nb, ng * nb, 1.0, Xg[:, c * nb:], Xg[:, c * nb:], 1.0,
+            for k in range(rank, nblk, world):
+                Xrow[:, k * nb:(k + 1) * nb].copy_(Wd[k])
+                for j in range(k - 1, -1, -1):  # W_kj = -(sum_{i=j+1..k} W_ki L_ij) inv(L_jj)
+                    ops.gemm(False, False, nb, nb, (k - j) * nb, 1.0, Xrow[:, (j + 1) * nb:], Lcols[j], 0.0, tmpb)
+                    ops.gemm(False, False, nb, nb, nb, -1.0, tmpb, Wd[j], 0.0, Xrow[:, j * nb:])
+                for c in range(k + 1):  # lower block columns of W_k^T W_k
+                    ops.gemm(True, False, (k + 1 - c) * nb, nb, nb, 1.0, Xrow[:, c * nb:], Xrow[:, c * nb:], 1.0,
                              Kinv[c * nb:, c * nb:])
             if rank == 0:  # G = alpha alpha^T - K^-1: the rank-1 term once
                 ops.gemm(False, True, N, N, 2, -1.0, alpha, alpha, 1.0, Kinv)
