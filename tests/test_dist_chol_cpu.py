@@ -79,7 +79,7 @@ def _worker(rank, world, port, grid, q):
         ds = onp.synthetic_exact_dataset(N, d=3)
         out[(N, nb, la)] = distributed_gpr_nlml(CpuOpsDouble(), ds["X"], ds["Y"], ds["theta"], ds["noise"], nbd=nb, grid=grid,
                                                 lookahead=la)
-    for N, nb in ((96, 16), (150, 32)):  # value + gradient (ragged N pads the last block)
+    for N, nb in ((96, 16), (150, 32), (200, 8)):  # value + gradient (ragged N pads the last block; 25 blocks: many owned rows)
         ds = onp.synthetic_exact_dataset(N, d=3)
         v, g = distributed_gpr_nlml(CpuOpsDouble(), ds["X"], ds["Y"], ds["theta"], ds["noise"], nbd=nb, grid=grid, want_grad=True)
         out[("grad", N, nb)] = (v, g.tolist())
