@@ -288,7 +288,7 @@ def run_mine(args):
         # per 53-point problem 518 useful DMMA (16 sub-partition cycles each) + 4 242 scalar FP64 warp-instructions (2 each);
         # the algorithmic N^3 + 4 N^2 flops are ~1/3 of that work, so `frac` cannot exceed ~0.30 at N = 53.
         if clocks.get("sm_mhz"):
-            cyc = kernel_sec * clocks["sm_mhz"] * 1e6 * h.sm_count() / nprob
+            cyc = kernel_sec * clocks["sm_mhz"] * 1e6 * int(h.sm_count) / nprob
             full = (518 * 16 + 4242 * 2) / 4.0
             line["roofline"]["pipe_model"] = {"sm_cycles_per_bin_measured": cyc, "sm_cycles_per_bin_fp64_pipe_only": full,
                                               "fp64_pipe_busy_est": full / cyc,
