@@ -38,6 +38,11 @@ constexpr int MAX_WPC = 12;
 // MFGP_V4_COOP_DIAG=1 selects a cooperative (shuffle-based) factorisation of the 8x8 diagonal tiles: 128 instead of 212
 // FP64-pipe instructions per tile, but 6 shuffles on the critical path of each of its 8 steps.  Measured: 766 k evals/s against
 // 790 k for the redundant per-lane version, so the default stays 0 (both pass the parity suite, same checksums).
+// Tiles assembled per loop iteration (2 * n independent exp chains per lane).  Measured: 2 -> 791 k, 4 -> 783 k, 7 -> 760 k
+// evals/s: more chains only add register pressure at the 168-register cap.
+#ifndef MFGP_V4_TILES_PER_ITER
+#define MFGP_V4_TILES_PER_ITER 2
+#endif
 #ifndef MFGP_V4_COOP_DIAG
 #define MFGP_V4_COOP_DIAG 0
 #endif
@@ -198,33 +203,33 @@ __global__ void __launch_bounds__(MAX_WPC * 32, 1) gpr_small_v4_kernel(SmallArgs
 
         // ---- 1: covariance tiles --------------------------------------------------------------------
         {
+            constexpr int TPI = MFGP_V4_TILES_PER_ITER;  // tiles per iteration = 2 * TPI independent exp chains per lane
             int i = 0, j = 0;
 #pragma unroll 1
-            for (int s = 0; s < NTRI; s += 2) {
-                const int ia = i, ja = j;
-                next_tile<NT>(i, j);
-                const bool two = (s + 1 < NTRI);
-                const int ib = two ? i : ia, jb = two ? j : ja;
-                next_tile<NT>(i, j);
-                double ka0, ka1, kb0, kb1;
-                kl_tile<NT, 0>(m, etab, d, ia, ja, g, t, ka0, ka1, nullptr, nullptr, nullptr);
-                kl_tile<NT, 0>(m, etab, d, ib, jb, g, t, kb0, kb1, nullptr, nullptr, nullptr);
-                if (p.grad) {  // K^L is needed again by the gradient: park it in the L2-resident scratch (own lane's values)
-                    __stcg(reinterpret_cast<double2*>(scr + s * 64), make_double2(ka0, ka1));
-                    if (two) __stcg(reinterpret_cast<double2*>(scr + (s + 1) * 64), make_double2(kb0, kb1));
+            for (int s = 0; s < NTRI; s += TPI) {
+                int ti[TPI], tj[TPI];
+                double k0[TPI], k1[TPI];
+#pragma unroll
+                for (int u = 0; u < TPI; ++u) {
+                    const bool live = (s + u < NTRI);
+                    ti[u] = live ? i : 0;  // tail of the last iteration: recompute tile 0, discard
+                    tj[u] = live ? j : 0;
+                    if (live) next_tile<NT>(i, j);
                 }
-                if (ia == ja) {  // diagonal: + noise (real rows) or identity (padding rows keep the factorisation well posed)
-                    const double dg = (8 * ia + g < N) ? noise : 1.0;
-                    if (g == 2 * t) ka0 += dg;
-                    if (g == 2 * t + 1) ka1 += dg;
+#pragma unroll
+                for (int u = 0; u < TPI; ++u) kl_tile<NT, 0>(m, etab, d, ti[u], tj[u], g, t, k0[u], k1[u], nullptr, nullptr, nullptr);
+#pragma unroll
+                for (int u = 0; u < TPI; ++u) {
+                    if (s + u >= NTRI) break;
+                    // K^L is needed again by the gradient: park it in the L2-resident scratch (own lane's values)
+                    if (p.grad) __stcg(reinterpret_cast<double2*>(scr + (s + u) * 64), make_double2(k0[u], k1[u]));
+                    if (ti[u] == tj[u]) {  // diagonal: + noise (real rows) or identity (padding rows keep the factorisation well posed)
+                        const double dg = (8 * ti[u] + g < N) ? noise : 1.0;
+                        if (g == 2 * t) k0[u] += dg;
+                        if (g == 2 * t + 1) k1[u] += dg;
+                    }
+                    *reinterpret_cast<double2*>(m.tiles + (s + u) * 64 + cst) = make_double2(k0[u], k1[u]);
                 }
-                if (ib == jb) {
-                    const double dg = (8 * ib + g < N) ? noise : 1.0;
-                    if (g == 2 * t) kb0 += dg;
-                    if (g == 2 * t + 1) kb1 += dg;
-                }
-                *reinterpret_cast<double2*>(m.tiles + s * 64 + cst) = make_double2(ka0, ka1);
-                if (two) *reinterpret_cast<double2*>(m.tiles + (s + 1) * 64 + cst) = make_double2(kb0, kb1);
             }
         }
         __syncwarp();
