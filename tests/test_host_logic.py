@@ -221,3 +221,61 @@ def test_svgp_flat_parameter_layout_matches_the_c_abi():
                                            num_outputs=P)
     with pytest.raises(NotImplementedError):
         shared._flat_parameters(d)  # one shared lengthscale: the device loop refuses instead of silently training d copies
+
+
+class _FakeHandle:
+    """Stand-in for _lib.Handle in HOST-LOGIC tests only (records calls, returns synthetic numbers; no arithmetic claims)."""
+
+    def __init__(self):
+        self.calls = []
+
+    def gpr_batched_nlml_grad(self, X, Y, thetas, noises, want_grad=True, **kw):
+        self.calls.append(("eval", thetas.shape, Y.shape))
+        nlml = thetas[:, 0] * 10.0 + np.arange(thetas.shape[0]) % Y.shape[1]  # depends on rho and on the bin
+        return nlml, None
+
+    def gpr_batched_adam(self, X, Y, u, m, v, noises, lr_t, b1, b2, eps, fix_rho=False, loss_hist=None, theta_out=None, info=None):
+        self.calls.append(("adam", u.shape, len(lr_t), fix_rho))
+        u -= 0.01 * len(lr_t)  # "training": every unconstrained variable moves the same way
+        loss_hist[:] = np.arange(len(lr_t))[:, None] + np.arange(u.shape[0])[None, :]
+        return loss_hist, theta_out
+
+    def gpr_predict(self, X, y, Xnew, theta, noise):
+        self.calls.append(("predict", y.shape, tuple(theta[:1])))
+        return np.full((Xnew.shape[0], 1), theta[0]), np.full(Xnew.shape[0], noise)
+
+
+def test_multibin_host_logic_with_fake_handle():
+    """MultiBinMFGP: restart 0 starts at the reference's initial values, problem b = r * P + p, moments / step count carry over,
+    best-restart selection ignores non-finite losses, predictions use each bin's best hyper-parameters."""
+    from multi_fidelity_gpflow_b200.multibin import MultiBinMFGP
+
+    rng = np.random.default_rng(0)
+    X = np.hstack([rng.random((20, 3)), (np.arange(20) >= 15).astype(float)[:, None]])
+    Y = rng.standard_normal((20, 4))
+    fh = _FakeHandle()
+    mdl = MultiBinMFGP(X, Y, num_restarts=3, seed=5, handle=fh)
+    th = mdl.thetas
+    assert th.shape == (3, 4, 9)
+    np.testing.assert_allclose(th[0], 1.0, rtol=1e-14)           # restart 0: rho = lengthscales = variances = 1
+    assert np.all(th[1:] > 0) and not np.allclose(th[1], th[2])   # perturbed restarts, all positive
+    assert np.array_equal(MultiBinMFGP(X, Y, num_restarts=3, seed=5, handle=fh).u, mdl.u)  # seeded
+    u0 = mdl.u.copy()
+    mdl.optimize(max_iters=7, learning_rate=0.1)
+    mdl.optimize(max_iters=5, learning_rate=0.1, use_cosine_decay=True)
+    assert mdl.iterations == 12 and mdl.loss_history.shape == (12, 3, 4)
+    assert [c for c in fh.calls if c[0] == "adam"] == [("adam", (12, 9), 7, False), ("adam", (12, 9), 5, False)]
+    np.testing.assert_allclose(mdl.u, u0 - 0.12)
+    # loss_history[s, r, p] is problem b = r * P + p of the flat batch
+    np.testing.assert_array_equal(mdl.loss_history[:7, 2, 1], np.arange(7) + (2 * 4 + 1))
+    # selection: lowest NLML per bin; the fake loss grows with rho, so the restart with the smallest rho wins every bin
+    best = mdl.best_restart()
+    assert np.array_equal(best, np.argmin(mdl.thetas[:, :, 0] * 10.0, axis=0))
+    mean, var = mdl.predict_f(X[:5])
+    assert mean.shape == (5, 4) and var.shape == (5, 4)
+    np.testing.assert_allclose(mean[0], mdl.best_thetas()[:, 0])  # each bin predicted with its own best theta
+    frozen = MultiBinMFGP(X, Y, num_restarts=1, use_rho=False, handle=fh)
+    frozen.optimize(max_iters=2)
+    assert fh.calls[-1] == ("adam", (4, 9), 2, True)
+    with pytest.raises(ValueError):
+        MultiBinMFGP(np.zeros((65, 3)), np.zeros((65, 1)), handle=fh)  # the small-matrix kernel is N <= 64
