@@ -113,6 +113,11 @@ typedef struct {
     double scale;   /* num_data / B, or 1 (singlebin_svgp.py passes no num_data) */
     double kl_mult; /* loss = -ELBO + (kl_mult - 1) KL   (linear_svgp.py:188) */
     double jitter;  /* gpflow default_jitter() = 1e-6 */
+    double lik_lower; /* lower bound of the likelihood-variance transform, used by mfgp_svgp_adam only: gpflow Gaussian
+                       * positive(lower=1e-6); HeteroscedasticGaussian positive() = 0 (linear_svgp.py:240) */
+    int masked;     /* 1: entries of Y that are NaN are missing outputs and contribute nothing (MaskedGaussian,
+                     * notebooks/"demo: missing output.ipynb" cell 2); exclusive with hetero */
+    int lik_per_output; /* 1: the likelihood variance is a [P] vector, one per output (same notebook: variance=np.ones(P)) */
 } mfgp_svgp_cfg;
 
 /* Forward + hand-derived backward.  Outputs (any grad pointer may be NULL to skip all
@@ -124,6 +129,13 @@ int mfgp_svgp_elbo_grad(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* 
                         const double* q_sqrt, double lik_var, double* elbo, double* kl,
                         double* gZ, double* gtheta, double* gW, double* gqmu, double* gqsqrt,
                         double* glik);
+/* Same with the likelihood variance passed by pointer (host or device): lik_var and glik hold 1 value, or P values when
+ * cfg->lik_per_output is set.  mfgp_svgp_elbo_grad is the scalar-by-value convenience form of this call. */
+int mfgp_svgp_elbo_grad_v(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* X, const double* Y,
+                          const double* Z, const double* theta, const double* W, const double* q_mu,
+                          const double* q_sqrt, const double* lik_var, double* elbo, double* kl,
+                          double* gZ, double* gtheta, double* gW, double* gqmu, double* gqsqrt,
+                          double* glik);
 /* mean [Ns, P], var [Ns, P]  (cfg->B is ignored, Ns rows are predicted). */
 int mfgp_svgp_predict(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* Xs, int Ns,
                       const double* Z, const double* theta, const double* W, const double* q_mu,
@@ -132,14 +144,36 @@ int mfgp_svgp_predict(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* Xs
 /* Training loop on the device for the SVGP models: the optimize() loops of mfgpflow/singlebin_svgp.py:
  * 64-97 and mfgpflow/linear_svgp.py:153-203 -- full-batch, Keras Adam (+ CosineDecay folded into lr_t, see
  * mfgp_gpr_batched_adam), loss = -ELBO + (kl_mult - 1) KL -- nsteps steps without a host round trip.
- * Flat parameter layout (doubles): [theta L*(2d+3)] [Z M*(d+1)] [W P*L, only if has_W] [q_mu M*L] [q_sqrt L*M*M] [lik_var 1].
- * u holds the UNCONSTRAINED values in that layout (theta = softplus(u), lik_var = 1e-6 + softplus(u), the rest identity;
+ * Flat parameter layout (doubles): [theta L*(2d+3)] [Z M*(d+1)] [W P*L, only if has_W] [q_mu M*L] [q_sqrt L*M*M] [lik_var 1, or P with
+ * cfg->lik_per_output].
+ * u holds the UNCONSTRAINED values in that layout (theta = softplus(u), lik_var = cfg->lik_lower + softplus(u), the rest identity;
  * the strictly upper part of every q_sqrt matrix must be zero and stays zero); u, m, v are updated in place.
  * mask (n bytes or NULL): 0 freezes an entry (not in trainable_variables).  loss_hist / kl_hist [nsteps] or NULL receive
  * the loss and KL evaluated BEFORE each update (the reference's loss_history / kl_history). */
 int mfgp_svgp_adam(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* X, const double* Y, int has_W, double* u,
                    double* m, double* v, const unsigned char* mask, const double* lr_t, double beta1, double beta2,
                    double eps, int nsteps, double* loss_hist, double* kl_hist);
+
+/* Data-parallel SVGP training step on device memory only (rows of the minibatch shard across one
+ * process per GPU, ONE all-reduce of the flat gradient; reference loops singlebin_svgp.py:79-85, linear_svgp.py:181-190).
+ * Per step every rank runs, on the handle's stream and without any host synchronisation:
+ *     mfgp_svgp_constrain(u -> c);  mfgp_svgp_elbo_grad_flat(rows of this rank, c -> eg);
+ *     all-reduce(sum) of eg [2 + n] in place (the caller's collective: ncclAllReduce on the same stream);
+ *     mfgp_svgp_adam_update(u, m, v <- eg).
+ * n = mfgp_svgp_flat_size() doubles in the flat layout of mfgp_svgp_adam.  All pointers are DEVICE pointers.
+ * eg after mfgp_svgp_elbo_grad_flat: eg[0] = cfg->scale * VE of this rank's rows, eg[1] = KL / nranks, eg[2 + i] = d/d c_i of
+ * (-scale VE_rank + kl_mult / nranks KL); after the all-reduce: [scale VE, KL, gradient of -ELBO + (kl_mult - 1) KL].
+ * The gradient pieces are written by the kernels straight into eg: no host staging, no concatenation.
+ * cfg->B is the number of rows of THIS call; cfg->scale = num_data / (global batch size). */
+long mfgp_svgp_flat_size(const mfgp_svgp_cfg* cfg, int has_W);
+int mfgp_svgp_constrain(mfgp_handle* h, const mfgp_svgp_cfg* cfg, int has_W, const double* u, double* c);
+int mfgp_svgp_elbo_grad_flat(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* X, const double* Y, int has_W,
+                             const double* c, int nranks, double* eg /* [2 + n] */);
+/* Keras-Adam update from the all-reduced eg; lr_t [nsteps] and the step counter *step live on the device (the counter is
+ * incremented by the call); loss_hist / kl_hist [nsteps] (device, or NULL) receive entry *step; scratch2: 2 doubles. */
+int mfgp_svgp_adam_update(mfgp_handle* h, const mfgp_svgp_cfg* cfg, int has_W, double* u, double* m, double* v,
+                          const unsigned char* mask, const double* c, const double* eg, const double* lr_t, int* step,
+                          double beta1, double beta2, double eps, double* loss_hist, double* kl_hist, double* scratch2);
 
 /* ---- dense fp64 building blocks (exported for tests / bench / comparators) ------------- */
 /* C[m,n] = alpha * op(A) op(B) + beta * C, row-major; transa/transb are 'N' or 'T'.

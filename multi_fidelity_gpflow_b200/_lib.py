@@ -51,8 +51,13 @@ def _load():
         "mfgp_gpr_batched_nlml_grad": ([vp, vp, i, i, vp, l, i, i, vp, vp, vp, vp, vp], i),
         "mfgp_gpr_batched_adam": ([vp, vp, i, i, vp, l, i, i, vp, vp, vp, vp, vp, d, d, d, i, i, vp, vp, vp], i),
         "mfgp_svgp_elbo_grad": ([vp, vp, vp, vp, vp, vp, vp, vp, vp, d, vp, vp, vp, vp, vp, vp, vp, vp], i),
+        "mfgp_svgp_elbo_grad_v": ([vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp], i),
         "mfgp_svgp_predict": ([vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp], i),
         "mfgp_svgp_adam": ([vp, vp, vp, vp, i, vp, vp, vp, vp, vp, d, d, d, i, vp, vp], i),
+        "mfgp_svgp_flat_size": ([vp, i], l),
+        "mfgp_svgp_constrain": ([vp, vp, i, vp, vp], i),
+        "mfgp_svgp_elbo_grad_flat": ([vp, vp, vp, vp, i, vp, i, vp], i),
+        "mfgp_svgp_adam_update": ([vp, vp, i, vp, vp, vp, vp, vp, vp, vp, vp, d, d, d, vp, vp, vp], i),
         "mfgp_gemm": ([vp, C.c_char, C.c_char, i, i, i, d, vp, l, vp, l, d, vp, l], i),
         "mfgp_potrf": ([vp, vp, i, l], i),
         "mfgp_potrf_inv": ([vp, vp, i, l, vp, l], i),
@@ -69,7 +74,8 @@ _lib = _load()
 EXPORTED_SYMBOLS = [
     "mfgp_version", "mfgp_create", "mfgp_destroy", "mfgp_set_stream", "mfgp_reset_stream", "mfgp_set_async", "mfgp_sync",
     "mfgp_last_error", "mfgp_sm_count", "mfgp_cov", "mfgp_cov_diag", "mfgp_cov_grad", "mfgp_gpr_nlml", "mfgp_gpr_nlml_grad",
-    "mfgp_gpr_predict", "mfgp_gpr_batched_nlml_grad", "mfgp_gpr_batched_adam", "mfgp_svgp_elbo_grad", "mfgp_svgp_predict", "mfgp_svgp_adam", "mfgp_gemm",
+    "mfgp_gpr_predict", "mfgp_gpr_batched_nlml_grad", "mfgp_gpr_batched_adam", "mfgp_svgp_elbo_grad", "mfgp_svgp_elbo_grad_v", "mfgp_svgp_predict", "mfgp_svgp_adam",
+    "mfgp_svgp_flat_size", "mfgp_svgp_constrain", "mfgp_svgp_elbo_grad_flat", "mfgp_svgp_adam_update", "mfgp_gemm",
     "mfgp_potrf", "mfgp_potrf_inv", "mfgp_fp64_peak",
 ]
 
@@ -77,7 +83,8 @@ EXPORTED_SYMBOLS = [
 class SvgpCfg(C.Structure):
     _fields_ = [
         ("L", C.c_int), ("M", C.c_int), ("P", C.c_int), ("B", C.c_int), ("d", C.c_int), ("hetero", C.c_int),
-        ("scale", C.c_double), ("kl_mult", C.c_double), ("jitter", C.c_double),
+        ("scale", C.c_double), ("kl_mult", C.c_double), ("jitter", C.c_double), ("lik_lower", C.c_double),
+        ("masked", C.c_int), ("lik_per_output", C.c_int),
     ]
 
 
@@ -209,7 +216,9 @@ class Handle:
 
     def gpr_batched_nlml_grad(self, X, Y, thetas, noises, nlml=None, grad=None, info=None, want_grad=True):
         """Host arrays or device tensors.  Y is [N, ycols]; B = thetas.shape[0] problems, problem b uses
-        column b % ycols (B > ycols = several hyper-parameter sets per bin)."""
+        column b % ycols (B > ycols = several hyper-parameter sets per bin).  A non-positive Cholesky pivot raises
+        NotPositiveDefiniteError unless a per-problem `info` array (int32 [B]) is passed: then info[b] holds the 1-based
+        failing pivot of problem b (0 = ok), its nlml / grad are NaN, and the call returns normally."""
         X, Y, thetas, noises = as_f64(X), as_f64(Y), as_f64(thetas), as_f64(noises)
         N, d = X.shape[0], X.shape[1] - 1
         ycols = ldy = Y.shape[1]
@@ -221,16 +230,18 @@ class Handle:
         rc = _lib.mfgp_gpr_batched_nlml_grad(
             self._h, _ptr(X), N, d, _ptr(Y), ldy, ycols, B, _ptr(thetas), _ptr(noises), _ptr(nlml), _ptr(grad), _ptr(info)
         )
-        self._check(rc, "mfgp_gpr_batched_nlml_grad")
+        if not (rc > 0 and info is not None):  # with a per-problem info[] a failed Cholesky is that problem's status, not an error
+            self._check(rc, "mfgp_gpr_batched_nlml_grad")
         return nlml, grad
 
     def svgp_adam(self, X, Y, L, M, P, has_W, u, m, v, mask, lr_t, beta1, beta2, eps=1e-7, scale=1.0, kl_mult=1.0,
-                  hetero=False, jitter=1e-6):
+                  hetero=False, jitter=1e-6, lik_lower=1e-6, masked=False, lik_per_output=False):
         """len(lr_t) full-batch Adam steps on the device; u, m, v (flat layout of include/mfgp.h) are updated in place.
         Returns (loss_hist, kl_hist)."""
         X, Y, lr_t = as_f64(X), as_f64(Y), as_f64(lr_t)
         B, d = X.shape[0], X.shape[1] - 1
-        cfg = SvgpCfg(L, M, P, B, d, int(hetero), float(scale), float(kl_mult), float(jitter))
+        cfg = SvgpCfg(L, M, P, B, d, int(hetero), float(scale), float(kl_mult), float(jitter), float(lik_lower), int(masked),
+                      int(lik_per_output))
         n = int(lr_t.shape[0])
         loss, kl = np.empty(n), np.empty(n)
         mk = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
@@ -254,32 +265,39 @@ class Handle:
         rc = _lib.mfgp_gpr_batched_adam(self._h, _ptr(X), N, d, _ptr(Y), ldy, ycols, B, _ptr(u), _ptr(m), _ptr(v), _ptr(noises),
                                         _ptr(lr_t), float(beta1), float(beta2), float(eps), int(bool(fix_rho)), nsteps,
                                         _ptr(loss_hist), _ptr(theta_out), _ptr(info))
-        self._check(rc, "mfgp_gpr_batched_adam")
+        if not (rc > 0 and info is not None):  # per-problem status in info[]: the other problems' steps stand
+            self._check(rc, "mfgp_gpr_batched_adam")
         return loss_hist, theta_out
 
     # -- SVGP ----------------------------------------------------------------------------------
     def svgp_elbo_grad(self, X, Y, Z, thetas, W, q_mu, q_sqrt, lik_var, scale=1.0, kl_mult=1.0, hetero=False,
-                       jitter=1e-6, want_grad=True):
+                       jitter=1e-6, want_grad=True, masked=False):
+        """lik_var: scalar (Gaussian / HeteroscedasticGaussian) or a [P] vector (MaskedGaussian: one variance per output);
+        g_lik_var comes back as a float or a [P] array accordingly.  masked=True skips the NaN entries of Y."""
         X, Y, Z, thetas, q_mu, q_sqrt = map(as_f64, (X, Y, Z, thetas, q_mu, q_sqrt))
         W = None if W is None else as_f64(W)
         B, d = X.shape[0], X.shape[1] - 1
         M, L = q_mu.shape
         P = L if W is None else W.shape[0]
-        cfg = SvgpCfg(L, M, P, B, d, int(hetero), float(scale), float(kl_mult), float(jitter))
-        elbo, kl, glik = np.empty(1), np.empty(1), np.zeros(1)
+        per_out = np.ndim(lik_var) > 0 and np.size(lik_var) > 1
+        lv = np.ascontiguousarray(np.ravel(lik_var), dtype=np.float64)
+        if lv.size != (P if per_out else 1):
+            raise ValueError(f"lik_var must be a scalar or have one entry per output ({P}); got {lv.size}")
+        cfg = SvgpCfg(L, M, P, B, d, int(hetero), float(scale), float(kl_mult), float(jitter), 0.0, int(masked), int(per_out))
+        elbo, kl, glik = np.empty(1), np.empty(1), np.zeros(lv.size)
         if want_grad:
             gZ, gth, gqm, gqs = np.zeros((M, d + 1)), np.zeros((L, 2 * d + 3)), np.zeros((M, L)), np.zeros((L, M, M))
             gW = None if W is None else np.zeros((P, L))
         else:
             gZ = gth = gqm = gqs = gW = None
-        rc = _lib.mfgp_svgp_elbo_grad(
+        rc = _lib.mfgp_svgp_elbo_grad_v(
             self._h, C.byref(cfg), _ptr(X), _ptr(Y), _ptr(Z), _ptr(thetas), _ptr(W), _ptr(q_mu), _ptr(q_sqrt),
-            float(lik_var), _ptr(elbo), _ptr(kl), _ptr(gZ), _ptr(gth), _ptr(gW), _ptr(gqm), _ptr(gqs),
+            _ptr(lv), _ptr(elbo), _ptr(kl), _ptr(gZ), _ptr(gth), _ptr(gW), _ptr(gqm), _ptr(gqs),
             _ptr(glik) if want_grad else None,
         )
         self._check(rc, "mfgp_svgp_elbo_grad")
         return dict(elbo=float(elbo[0]), kl=float(kl[0]), g_Z=gZ, g_thetas=gth, g_W=gW, g_q_mu=gqm, g_q_sqrt=gqs,
-                    g_lik_var=float(glik[0]))
+                    g_lik_var=glik.copy() if per_out else float(glik[0]))
 
     def svgp_predict(self, Xs, Z, thetas, W, q_mu, q_sqrt, jitter=1e-6):
         Xs, Z, thetas, q_mu, q_sqrt = map(as_f64, (Xs, Z, thetas, q_mu, q_sqrt))
@@ -287,7 +305,7 @@ class Handle:
         Ns, d = Xs.shape[0], Xs.shape[1] - 1
         M, L = q_mu.shape
         P = L if W is None else W.shape[0]
-        cfg = SvgpCfg(L, M, P, Ns, d, 0, 1.0, 1.0, float(jitter))
+        cfg = SvgpCfg(L, M, P, Ns, d, 0, 1.0, 1.0, float(jitter), 0.0, 0, 0)
         mean, var = np.empty((Ns, P)), np.empty((Ns, P))
         rc = _lib.mfgp_svgp_predict(self._h, C.byref(cfg), _ptr(Xs), Ns, _ptr(Z), _ptr(thetas), _ptr(W), _ptr(q_mu),
                                     _ptr(q_sqrt), _ptr(mean), _ptr(var))

@@ -296,11 +296,10 @@ int mfgp_gpr_batched_nlml_grad(mfgp_handle* h, const double* X, int N, int d, co
     cudaSetDevice(h->device);
     if (B == 0) return 0;
     {
-        static const int which = [] { const char* e = getenv("MFGP_SMALL_KERNEL"); return e ? atoi(e) : 4; }();
         static const bool pipe = [] { const char* e = getenv("MFGP_BATCH_PIPELINE"); return !(e && e[0] == '0'); }();
         const bool host_io = !mfgp_is_device_ptr(theta) && !mfgp_is_device_ptr(noise) && !mfgp_is_device_ptr(nlml) &&
                              (!grad || !mfgp_is_device_ptr(grad)) && (!info || !mfgp_is_device_ptr(info));
-        if (pipe && which == 4 && host_io && N <= MFGP_SMALL_MAX_N && d <= MFGP_SMALL_MAX_D && B >= 16L * h->sm_count * 12)
+        if (pipe && host_io && N <= MFGP_SMALL_MAX_N && d <= MFGP_SMALL_MAX_D && B >= 16L * h->sm_count * 12)
             return batched_small_pipelined(h, X, N, d, Y, ldy, ycols, B, theta, noise, nlml, grad, info);
     }
     Scope sc(h);
@@ -316,8 +315,7 @@ int mfgp_gpr_batched_nlml_grad(mfgp_handle* h, const double* X, int N, int d, co
         SmallArgs a{};
         a.X = dX; a.N = N; a.d = d; a.Y = dY; a.ldy = ldy; a.ycols = ycols; a.B = B;
         a.theta = dth; a.noise = dnz; a.nlml = dn; a.grad = dg; a.info = di; a.d_info = h->d_info;
-        static const int which = [] { const char* e = getenv("MFGP_SMALL_KERNEL"); return e ? atoi(e) : 4; }();
-        if ((which == 1 ? launch_gpr_small(h->stream, a) : which == 2 ? launch_gpr_small_mma(h->stream, a) : launch_gpr_small_v4(h->stream, a)))
+        if (launch_gpr_small_v4(h->stream, a))
             return mfgp_fail(h, MFGP_ERR_CUDA, "gpr_small launch failed");
     } else {
         // blocked path, chunked so that 3 N^2 workspaces per problem fit comfortably

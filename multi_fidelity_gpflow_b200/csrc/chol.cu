@@ -11,6 +11,7 @@
 // These replace tf.linalg.cholesky / triangular_solve behind GPflow's GPR / SVGP objectives
 // (reference call sites linear.py:206, singlebin_svgp.py:83, linear_svgp.py:184).
 #include "chol.cuh"
+#include "common.cuh"
 
 #include <cstdlib>
 
@@ -33,7 +34,7 @@ struct DiagArgs {
     int* info_vec;
 };
 
-// ---- DMMA tile helpers (same swizzled 8x8-tile layout as gpr_small_mma.cu) ---------------------------
+// ---- DMMA tile helpers (same swizzled 8x8-tile layout as gpr_small_v4.cu) ---------------------------
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1)
@@ -300,11 +301,8 @@ __global__ void place_diag_kernel(const double* __restrict__ dinv, long stride_d
 
 int launch_potrf(cudaStream_t s, const CholArgs& a) {
     if (a.N <= 0 || a.batch <= 0) return 0;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM);
-        attr = true;
-    }
+    static SmemOptIn optin;
+    if (!optin.ensure(potrf_diag_kernel, DIAG_SMEM)) return -2;
     const int N = a.N;
     const int nblk = chol_nblk(N);
     const long stride_dinv = (long)nblk * NB * NB;

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "../../include/mfgp.h"
@@ -24,7 +25,6 @@ struct mfgp_handle {
     int sm_count = 148;
     int* d_info = nullptr;   // device: first failing pivot (1-based), 0 = ok
     int* h_info = nullptr;   // pinned mirror
-    const double* lik_var_dev = nullptr;  // when set, the SVGP likelihood variance is read from the device (training loop)
     char err[512] = {0};
 };
 
@@ -51,6 +51,46 @@ inline int mfgp_fail(mfgp_handle* h, int code, const char* fmt, ...) {
         int _rc = (expr);         \
         if (_rc != 0) return _rc; \
     } while (0)
+
+// ---- per-device launch state -------------------------------------------------------------------
+// Function attributes and device properties belong to a DEVICE, and one process may hold one handle per GPU
+// (include/mfgp.h threading contract): every cache below is a per-device table behind a mutex.
+constexpr int MFGP_MAX_DEVICES = 64;
+
+struct mfgp_dev_info {
+    int sms = 0;         // multiprocessors
+    int smem_optin = 0;  // cudaDevAttrMaxSharedMemoryPerBlockOptin
+};
+inline mfgp_dev_info mfgp_current_dev_info() {
+    static std::mutex mu;
+    static mfgp_dev_info tab[MFGP_MAX_DEVICES];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    mfgp_dev_info local;
+    mfgp_dev_info& e = (dev >= 0 && dev < MFGP_MAX_DEVICES) ? tab[dev] : local;
+    if (!e.sms) {
+        cudaDeviceGetAttribute(&e.sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&e.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    return e;
+}
+// Raises cudaFuncAttributeMaxDynamicSharedMemorySize of one kernel to >= bytes on the CURRENT device, once per device.
+struct SmemOptIn {
+    std::mutex mu;
+    int have[MFGP_MAX_DEVICES] = {};
+    template <typename Kernel>
+    bool ensure(Kernel func, size_t bytes) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lock(mu);
+        const bool cached = dev >= 0 && dev < MFGP_MAX_DEVICES;
+        if (cached && (int)bytes <= have[dev]) return true;
+        if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return false;
+        if (cached) have[dev] = (int)bytes;
+        return true;
+    }
+};
 
 inline bool mfgp_is_device_ptr(const void* p) {
     cudaPointerAttributes a;
@@ -130,7 +170,10 @@ struct Scope {
     }
     // copy results back, synchronise unless (async && no host outputs), collect info
     int finish() {
-        if (!ok) return mfgp_fail(h, MFGP_ERR_CUDA, "%s", h->err[0] ? h->err : "allocation / staging failed");
+        if (!ok) {
+            if (!h->err[0]) snprintf(h->err, sizeof(h->err), "allocation / staging failed");
+            return MFGP_ERR_CUDA;  // h->err already holds the message of the failing allocation / copy
+        }
         for (auto& o : outs) CUDA_TRY(h, cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaGetLastError());
         if (h->async && !host_out) return 0;

@@ -14,6 +14,7 @@
 // so both the direct store (row segments) and the mirrored store of the symmetric case
 // (column segments) are written as full 128-byte lines with 128-bit STG.
 #include "cov.cuh"
+#include "common.cuh"
 
 #include "mathx.cuh"
 
@@ -726,20 +727,12 @@ static int launch_cov_stream(cudaStream_t s, const CovArgs& a, int TI, int TJ, l
     q.K = a.K; q.ldk = a.ldk; q.strideK = a.strideK;
     q.symmetric = a.symmetric; q.mirror = a.mirror; q.vec_ok = vec_ok;
     q.diag_add = a.diag_add; q.diag_add_vec = a.diag_add_vec;
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = mfgp_current_dev_info().sms;
     const size_t smem = (size_t)(64 + 4 * S * T + 8 * 32 * 18) * sizeof(double);
-    static size_t attr = 0;
-    if (smem > attr) {
-        if (cudaFuncSetAttribute(cov_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaFreeAsync(ws, s);
-            return -2;
-        }
-        attr = smem;
+    static SmemOptIn optin;
+    if (!optin.ensure(cov_stream_kernel, smem)) {
+        cudaFreeAsync(ws, s);
+        return -2;
     }
     // contiguous chunks of tiles per CTA; measured at N = 32 768: 8 chunks per resident CTA slot / <= 64 tiles 3930 GB/s,
     // 32 / <= 16 tiles 4057 GB/s (shorter tail, better balance between the two dies)
@@ -765,11 +758,8 @@ int launch_cov(cudaStream_t s, const CovArgs& a) {
     static const int stream_min = [] { const char* e = getenv("MFGP_COV_STREAM_MIN_TILES"); return e ? atoi(e) : 1024; }();
     if (ntiles * a.batch >= stream_min) return launch_cov_stream(s, a, TI, TJ, ntiles, vec_ok);
     const size_t smem = tile_smem_bytes(a.d);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(MFGP_MAX_D));
-        attr_set = true;
-    }
+    static SmemOptIn optin;
+    if (!optin.ensure(cov_kernel, tile_smem_bytes(MFGP_MAX_D))) return -2;
     dim3 grid((unsigned)ntiles, 1, a.batch);
     cov_kernel<<<grid, 256, smem, s>>>(a, TJ, vec_ok);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
@@ -796,13 +786,9 @@ int launch_cov_grad(cudaStream_t s, const CovGradArgs& a) {
     const int TJ = (a.Nb + COV_TILE - 1) / COV_TILE;
     const long ntiles = grad_ntiles(a);
     const size_t smem = tile_smem_bytes(a.d) + (size_t)8 * (2 * a.d + 4) * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
-        const int mx = (int)(tile_smem_bytes(MFGP_MAX_D) + 8 * (2 * MFGP_MAX_D + 4) * 8);
-        cudaFuncSetAttribute(cov_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        cudaFuncSetAttribute(cov_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        attr_set = true;
-    }
+    static SmemOptIn optin_rg, optin_norg;
+    const size_t mx = tile_smem_bytes(MFGP_MAX_D) + 8 * (2 * MFGP_MAX_D + 4) * 8;
+    if (!(a.rowgrad ? optin_rg.ensure(cov_grad_kernel<true>, mx) : optin_norg.ensure(cov_grad_kernel<false>, mx))) return -2;
     dim3 grid((unsigned)ntiles, 1, a.batch);
     if (a.rowgrad) cov_grad_kernel<true><<<grid, 256, smem, s>>>(a, TJ, ntiles);
     else cov_grad_kernel<false><<<grid, 256, smem, s>>>(a, TJ, ntiles);

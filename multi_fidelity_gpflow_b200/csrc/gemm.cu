@@ -12,6 +12,7 @@
 // Warp tile 64x32 (128x128 CTA, 8 warps) or 32x32 (64x64 CTA, 4 warps): 12 (8) LDS.64 per
 // 32 (16) DMMA.  Triangular operands are expressed as per-tile k ranges (GemmKRange).
 #include "gemm.cuh"
+#include "common.cuh"
 
 #include <cstdint>
 
@@ -255,11 +256,8 @@ template <int BM, int BN, int WM, int WN, bool TA, bool TB>
 int launch_cfg(cudaStream_t s, const GemmArgs& a, const KernelArgs& ka) {
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
     constexpr int SMEM = STAGES * (BM + BN) * BK * 8;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(dgemm_kernel<BM, BN, WM, WN, TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-        attr = true;
-    }
+    static SmemOptIn optin;
+    if (!optin.ensure(dgemm_kernel<BM, BN, WM, WN, TA, TB>, SMEM)) return -2;
     dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, a.batch * a.batch2);
     dgemm_kernel<BM, BN, WM, WN, TA, TB><<<grid, NT, SMEM, s>>>(ka);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;

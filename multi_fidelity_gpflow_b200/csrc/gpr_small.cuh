@@ -1,4 +1,4 @@
-// gpr_small.cuh -- batched small-matrix GPR NLML+grad (one CTA per problem).
+// gpr_small.cuh -- batched small-matrix GPR NLML+grad (K6: one warp per problem, persistent grid).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -22,6 +22,4 @@ struct SmallArgs {
     int prob0;            // v4: index of this launch's first problem in the caller's batch (selects the Y column)
     double* scratch;      // v4: K^L of every problem in flight (L2-resident), filled by the launcher
 };
-int launch_gpr_small(cudaStream_t s, const SmallArgs& a);      // v1: one CTA per problem (DFMA)
-int launch_gpr_small_mma(cudaStream_t s, const SmallArgs& a);  // v2: one warp per problem (DMMA tiles)
-int launch_gpr_small_v4(cudaStream_t s, const SmallArgs& a);   // v4: persistent, compact code, 12 warps per SM
+int launch_gpr_small_v4(cudaStream_t s, const SmallArgs& a);  // persistent grid, one warp per problem, 12 warps per SM

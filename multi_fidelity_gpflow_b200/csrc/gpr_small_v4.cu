@@ -1,7 +1,7 @@
 // gpr_small_v4.cu -- K6 v4: batched small-matrix NLML + analytic gradient, one warp per problem,
 // PERSISTENT grid, compact instruction stream, 12 problems in flight per SM.
 //
-// What changed against v2/v3 (gpr_small_mma.cu), and why (profiles/r01_ncu_gpr_small_final.csv):
+// What changed against v2/v3 (deleted; see git history), and why (profiles/r01_ncu_gpr_small_final.csv):
 //   * v3's fully unrolled body is ~300 KB of SASS; with 8 warps at 8 different program counters the dominant
 //     stall was `no_instruction` (2.0 cycles per issued instruction) and the 234 registers capped the SM at 8 warps.
 //     Here the covariance assembly / dK recompute (the exp-heavy part) and the 8x8 diagonal-tile factorisation are
@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstdint>
 
+#include "common.cuh"
 #include "gpr_small.cuh"
 #include "mathx.cuh"
 
@@ -696,24 +697,17 @@ __global__ void __launch_bounds__(MAX_WPC * 32, 1) gpr_small_v4_kernel(SmallArgs
 template <int NT, int DS>
 int launch_v4(cudaStream_t st, const SmallArgs& a) {
     const int wd = (int)((WarpMem<NT>::doubles(a.d) + 1) & ~(size_t)1);  // every warp's base stays 16-byte aligned
-    static int smem_cap = 0, sms = 0, attr_bytes = -1;
-    if (!smem_cap) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    }
+    const mfgp_dev_info di = mfgp_current_dev_info();
+    const int smem_cap = di.smem_optin, sms = di.sms;
+    if (smem_cap <= 0 || sms <= 0) return -2;
     int wpc = (int)(((size_t)smem_cap - 64 * 8) / ((size_t)wd * 8));
     if (wpc > MAX_WPC) wpc = MAX_WPC;
     if (wpc < 1) return -1;
     const int want_warps = a.B < sms * wpc ? a.B : sms * wpc;  // few problems: spread them over the SMs first
     if ((want_warps + sms - 1) / sms < wpc) wpc = (want_warps + sms - 1) / sms;
     const size_t bytes = (size_t)wd * 8 * wpc + 64 * 8;
-    if ((int)bytes > attr_bytes) {
-        if (cudaFuncSetAttribute(gpr_small_v4_kernel<NT, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
-            return -2;
-        attr_bytes = (int)bytes;
-    }
+    static SmemOptIn optin;
+    if (!optin.ensure(gpr_small_v4_kernel<NT, DS>, bytes)) return -2;
     const int want = (a.B + wpc - 1) / wpc;
     const int grid = want < sms ? want : sms;
     SmallArgs b = a;

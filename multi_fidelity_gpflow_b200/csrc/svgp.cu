@@ -75,14 +75,18 @@ __global__ void col_reduce_kernel(const double* __restrict__ A, const double* __
 }
 
 // One thread per (n, p).  mode 0: ELBO (writes adjoints fbm/fbv [P][B] + per-block partial sums),
-// mode 1: predict (writes mean/var [B][P]).
+// mode 1: predict (writes mean/var [B][P]).  Likelihood epilogues (cfg->hetero / masked / lik_per_output):
+//   Gaussian                 var_eff = lik_var[0]                                   (gpflow Gaussian)
+//   HeteroscedasticGaussian  var_eff = lik_var[0] + Y_unc^2, Y = [Y_obs | Y_unc]    (linear_svgp.py:243-267)
+//   MaskedGaussian           var_eff = lik_var[p]; entries with Y = NaN contribute nothing
+//                            (reference notebooks/"demo: missing output.ipynb" cell 2, class MaskedGaussian)
+// lbuf (per-output variances only): d(-ve)/d var_eff per entry, reduced per output by lik_grad_kernel.
 __global__ void mix_ve_kernel(int mode, const double* __restrict__ g_mean, const double* __restrict__ g_var, int L,
                               int B, int P, const double* __restrict__ W, const double* __restrict__ Y, int hetero,
-                              double lik_var, double scale, double* __restrict__ fbm, double* __restrict__ fbv,
-                              double* __restrict__ part, double* __restrict__ mean, double* __restrict__ var,
-                              const double* __restrict__ lik_var_dev = nullptr) {
+                              int masked, const double* __restrict__ lik_var, int per_out, double scale,
+                              double* __restrict__ fbm, double* __restrict__ fbv, double* __restrict__ part,
+                              double* __restrict__ lbuf, double* __restrict__ mean, double* __restrict__ var) {
     __shared__ double sh[8];
-    if (lik_var_dev) lik_var = *lik_var_dev;
     const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
     double ve = 0.0, lb = 0.0;
     if (idx < (long)B * P) {
@@ -106,17 +110,23 @@ __global__ void mix_ve_kernel(int mode, const double* __restrict__ g_mean, const
         } else {
             const long ldy = hetero ? 2L * P : P;
             const double y = Y[(long)n * ldy + p];
-            double ev = lik_var;
-            if (hetero) {
-                const double u = Y[(long)n * ldy + P + p];
-                ev = fma(u, u, ev);
+            double bm = 0.0, bv = 0.0;
+            if (!(masked && isnan(y))) {
+                double ev = lik_var[per_out ? p : 0];
+                if (hetero) {
+                    const double u = Y[(long)n * ldy + P + p];
+                    ev = fma(u, u, ev);
+                }
+                const double r = y - fm;
+                const double q = fma(r, r, fv);
+                ve = -0.5 * LOG2PI - 0.5 * log(ev) - 0.5 * q / ev;
+                lb = 0.5 / ev - 0.5 * q / (ev * ev);  // d(-ve)/d lik_var
+                bm = -scale * r / ev;
+                bv = scale * 0.5 / ev;
             }
-            const double r = y - fm;
-            const double q = fma(r, r, fv);
-            ve = -0.5 * LOG2PI - 0.5 * log(ev) - 0.5 * q / ev;
-            lb = 0.5 / ev - 0.5 * q / (ev * ev);  // d(-ve)/d lik_var
-            fbm[(long)p * B + n] = -scale * r / ev;
-            fbv[(long)p * B + n] = scale * 0.5 / ev;
+            fbm[(long)p * B + n] = bm;
+            fbv[(long)p * B + n] = bv;
+            if (lbuf) lbuf[(long)p * B + n] = lb;
         }
     }
     if (mode == 0) {
@@ -126,6 +136,16 @@ __global__ void mix_ve_kernel(int mode, const double* __restrict__ g_mean, const
             part[2 * blockIdx.x + 1] = b;
         }
     }
+}
+
+// glik[p] = scale * sum_n lbuf[p][n]   (per-output likelihood variances; one block per output, fixed summation order)
+__global__ void lik_grad_kernel(const double* __restrict__ lbuf, int B, double scale, double* __restrict__ glik) {
+    __shared__ double sh[8];
+    const int p = blockIdx.x;
+    double s = 0.0;
+    for (int n = threadIdx.x; n < B; n += blockDim.x) s += lbuf[(long)p * B + n];
+    s = block_sum256(s, sh);
+    if (threadIdx.x == 0) glik[p] = scale * s;
 }
 
 // gbar_mean[l][n] = sum_p fbm[p][n] W[p][l];  gbar_var[l][n] = sum_p fbv[p][n] W[p][l]^2
@@ -388,8 +408,20 @@ int mfgp_svgp_elbo_grad(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* 
                         double lik_var, double* elbo, double* kl, double* gZ, double* gtheta, double* gW,
                         double* gqmu, double* gqsqrt, double* glik) {
     if (!h) return MFGP_ERR_ARG;
-    if (!cfg || !X || !Y || !Z || !theta || !q_mu || !q_sqrt || !elbo || !kl)
+    if (cfg && cfg->lik_per_output)
+        return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_svgp_elbo_grad: per-output likelihood variances need mfgp_svgp_elbo_grad_v");
+    return mfgp_svgp_elbo_grad_v(h, cfg, X, Y, Z, theta, W, q_mu, q_sqrt, &lik_var, elbo, kl, gZ, gtheta, gW, gqmu, gqsqrt, glik);
+}
+
+int mfgp_svgp_elbo_grad_v(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* X, const double* Y, const double* Z,
+                          const double* theta, const double* W, const double* q_mu, const double* q_sqrt,
+                          const double* lik_var, double* elbo, double* kl, double* gZ, double* gtheta, double* gW,
+                          double* gqmu, double* gqsqrt, double* glik) {
+    if (!h) return MFGP_ERR_ARG;
+    if (!cfg || !X || !Y || !Z || !theta || !q_mu || !q_sqrt || !lik_var || !elbo || !kl)
         return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_svgp_elbo_grad: NULL argument");
+    if (cfg->hetero && cfg->masked)
+        return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_svgp_elbo_grad: hetero and masked likelihoods are exclusive");
     const int L = cfg->L, M = cfg->M, P = cfg->P, B = cfg->B, d = cfg->d;
     if (L < 1 || M < 1 || P < 1 || B < 1 || d < 1 || d > MFGP_MAX_D || (!W && L != P))
         return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_svgp_elbo_grad: bad configuration");
@@ -414,7 +446,9 @@ int mfgp_svgp_elbo_grad(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* 
     double* dgW = (want_grad && W) ? sc.out(gW, (size_t)P * L) : nullptr;
     double* dgqm = want_grad ? sc.out(gqmu, (size_t)M * L) : nullptr;
     double* dgqs = want_grad ? sc.out(gqsqrt, (size_t)L * M * M) : nullptr;
-    double* dglik = want_grad ? sc.out(glik, 1) : nullptr;
+    const int per_out = cfg->lik_per_output ? 1 : 0, nlik = per_out ? P : 1;
+    const double* dlv = sc.in(lik_var, nlik);
+    double* dglik = want_grad ? sc.out(glik, nlik) : nullptr;
     if (!sc.ok) return sc.finish();
 
     Fwd f;
@@ -426,9 +460,11 @@ int mfgp_svgp_elbo_grad(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* 
     double* part = sc.alloc<double>((size_t)2 * nblk);
     double* klpart = sc.alloc<double>(L);
     double* gth_ws = sc.alloc<double>((size_t)L * (2 * d + 4), true);
+    double* lbuf = (per_out && want_grad) ? sc.alloc<double>((size_t)P * B) : nullptr;
     if (!sc.ok) return sc.finish();
-    mix_ve_kernel<<<nblk, 256, 0, s>>>(0, f.g_mean, f.g_var, L, B, P, dW, dY, cfg->hetero, lik_var, cfg->scale, fbm, fbv,
-                                       part, nullptr, nullptr, h->lik_var_dev);
+    mix_ve_kernel<<<nblk, 256, 0, s>>>(0, f.g_mean, f.g_var, L, B, P, dW, dY, cfg->hetero, cfg->masked, dlv, per_out,
+                                       cfg->scale, fbm, fbv, part, lbuf, nullptr, nullptr);
+    if (lbuf) lik_grad_kernel<<<P, 256, 0, s>>>(lbuf, B, cfg->scale, dglik);
     kl_kernel<<<L, 256, 0, s>>>(dqm, f.Lq, M, f.ldM, L, klpart);
 
     if (want_grad) {
@@ -539,8 +575,8 @@ int mfgp_svgp_elbo_grad(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* 
         if (launch_cov_grad(s, cn)) return mfgp_fail(h, MFGP_ERR_CUDA, "svgp: cov_grad(Z,X) failed");
         knn_grad_kernel<<<L, 256, 0, s>>>(dX, B, d, dth, gbv, gth_ws);
     }
-    finalize_kernel<<<(L * (2 * d + 3) + 255) / 256, 256, 0, s>>>(part, nblk, klpart, L, cfg->scale, delbo, dkl, dglik,
-                                                                  gth_ws, d, dgth);
+    finalize_kernel<<<(L * (2 * d + 3) + 255) / 256, 256, 0, s>>>(part, nblk, klpart, L, cfg->scale, delbo, dkl,
+                                                                  per_out ? nullptr : dglik, gth_ws, d, dgth);
     return sc.finish();
 }
 
@@ -568,8 +604,8 @@ int mfgp_svgp_predict(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* Xs
     Fwd f;
     MFGP_TRY(svgp_forward(h, sc, L, M, Ns, d, cfg->jitter, dX, dZ, dth, dqm, dqs, f));
     const int nblk = (int)(((long)Ns * P + 255) / 256);
-    mix_ve_kernel<<<nblk, 256, 0, s>>>(1, f.g_mean, f.g_var, L, Ns, P, dW, nullptr, 0, 1.0, 1.0, nullptr, nullptr, nullptr,
-                                       dmean, dvar);
+    mix_ve_kernel<<<nblk, 256, 0, s>>>(1, f.g_mean, f.g_var, L, Ns, P, dW, nullptr, 0, 0, nullptr, 0, 1.0, nullptr, nullptr,
+                                       nullptr, nullptr, dmean, dvar);
     return sc.finish();
 }
 
@@ -581,18 +617,20 @@ int mfgp_svgp_predict(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* Xs
 // -ELBO + (kl_multiplier - 1) KL) without a host round trip per step.
 namespace {
 __device__ __forceinline__ double sp_fwd(double u) { return u > 0.0 ? u + log1p(exp(-u)) : log1p(exp(u)); }
-// segment boundaries of the flat layout: [0, n_theta) softplus; [n_theta, n - 1) identity; n - 1: 1e-6 + softplus
-__global__ void svgp_constrain_kernel(const double* __restrict__ u, double* __restrict__ c, long n, long n_theta) {
+// segments of the flat layout: [0, n_theta) softplus; [n_theta, o_lik) identity; [o_lik, n) lik_lower + softplus
+__global__ void svgp_constrain_kernel(const double* __restrict__ u, double* __restrict__ c, long n, long n_theta, long o_lik,
+                                      double lik_lower) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double x = u[i];
-    c[i] = i < n_theta ? sp_fwd(x) : (i == n - 1 ? 1e-6 + sp_fwd(x) : x);
+    c[i] = i < n_theta ? sp_fwd(x) : (i >= o_lik ? lik_lower + sp_fwd(x) : x);
 }
 __global__ void svgp_adam_kernel(double* __restrict__ u, double* __restrict__ m, double* __restrict__ v,
                                  const double* __restrict__ c, const double* __restrict__ g, const unsigned char* __restrict__ mask,
-                                 long n, long n_theta, const double* __restrict__ lr_t, const int* __restrict__ step_ptr, double b1,
-                                 double b2, double eps, const double* __restrict__ elbo_kl, double kl_mult,
-                                 double* __restrict__ loss_hist, double* __restrict__ kl_hist) {
+                                 long n, long n_theta, long o_lik, double lik_lower, const double* __restrict__ lr_t,
+                                 const int* __restrict__ step_ptr, double b1, double b2, double eps,
+                                 const double* __restrict__ elbo_kl, double kl_mult, double* __restrict__ loss_hist,
+                                 double* __restrict__ kl_hist) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const int step = *step_ptr;  // device-side step counter: the same captured graph is replayed for every step
     if (i == 0) {
@@ -601,8 +639,8 @@ __global__ void svgp_adam_kernel(double* __restrict__ u, double* __restrict__ m,
     }
     if (i >= n || (mask && !mask[i])) return;
     double gu = g[i];
-    if (i < n_theta) gu *= 1.0 - exp(-c[i]);                  // d softplus
-    else if (i == n - 1) gu *= 1.0 - exp(-(c[i] - 1e-6));     // lower bound 1e-6 (gpflow Gaussian likelihood)
+    if (i < n_theta) gu *= 1.0 - exp(-c[i]);                       // d softplus
+    else if (i >= o_lik) gu *= 1.0 - exp(-(c[i] - lik_lower));     // positive(lower): 1e-6 Gaussian, 0 Heteroscedastic
     double mi = m[i], vi = v[i];
     mi += (gu - mi) * (1.0 - b1);
     vi += (gu * gu - vi) * (1.0 - b2);
@@ -611,6 +649,39 @@ __global__ void svgp_adam_kernel(double* __restrict__ u, double* __restrict__ m,
     v[i] = vi;
 }
 __global__ void svgp_step_inc_kernel(int* step) { ++*step; }
+
+// data-parallel bookkeeping after one rank's evaluation: eg[0] <- elbo + kl = scale * VE_local, eg[1] <- kl / nranks, so that
+// an all-reduce(sum) over the ranks leaves [scale * VE, KL, gradient of -ELBO + (kl_mult - 1) KL]
+__global__ void svgp_dp_fix_kernel(double* eg, double inv_ranks) {
+    const double e = eg[0], k = eg[1];
+    eg[0] = e + k;
+    eg[1] = k * inv_ranks;
+}
+// loss / KL history from the all-reduced pair: -ELBO + (kl_mult - 1) KL with ELBO = eg[0] - eg[1]
+__global__ void svgp_dp_hist_kernel(const double* __restrict__ eg, double* __restrict__ ek) {
+    ek[0] = eg[0] - eg[1];
+    ek[1] = eg[1];
+}
+
+struct FlatLayout {
+    long n_theta, o_Z, o_W, o_qm, o_qs, o_lv, n;
+    FlatLayout(const mfgp_svgp_cfg* c, int has_W) {
+        n_theta = (long)c->L * (2 * c->d + 3);
+        o_Z = n_theta;
+        o_W = o_Z + (long)c->M * (c->d + 1);
+        o_qm = o_W + (has_W ? (long)c->P * c->L : 0);
+        o_qs = o_qm + (long)c->M * c->L;
+        o_lv = o_qs + (long)c->L * c->M * c->M;
+        n = o_lv + (c->lik_per_output ? c->P : 1);
+    }
+};
+
+struct AsyncGuard {  // nested library calls only enqueue; the caller's mode comes back on every exit path
+    mfgp_handle* h;
+    int was;
+    explicit AsyncGuard(mfgp_handle* hh) : h(hh), was(hh->async) { h->async = 1; }
+    ~AsyncGuard() { h->async = was; }
+};
 }  // namespace
 
 extern "C" int mfgp_svgp_adam(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* X, const double* Y, int has_W, double* u,
@@ -626,37 +697,35 @@ extern "C" int mfgp_svgp_adam(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const do
     cudaSetDevice(h->device);
     cudaStream_t s = h->stream;
     const long n_theta = (long)L * (2 * d + 3), n_Z = (long)M * (d + 1), n_W = has_W ? (long)P * L : 0, n_qm = (long)M * L,
-               n_qs = (long)L * M * M;
-    const long o_Z = n_theta, o_W = o_Z + n_Z, o_qm = o_W + n_W, o_qs = o_qm + n_qm, o_lv = o_qs + n_qs, n = o_lv + 1;
+               n_qs = (long)L * M * M, n_lv = cfg->lik_per_output ? P : 1;
+    const long o_Z = n_theta, o_W = o_Z + n_Z, o_qm = o_W + n_W, o_qs = o_qm + n_qm, o_lv = o_qs + n_qs, n = o_lv + n_lv;
     const int ycols = cfg->hetero ? 2 * P : P;
     int rc = 0;
+    Scope sc(h);
+    const double* dX = sc.in(X, (size_t)B * (d + 1));
+    const double* dY = sc.in(Y, (size_t)B * ycols);
+    const double* dlr = sc.in(lr_t, nsteps);
+    const unsigned char* dmask = mask ? sc.in(mask, (size_t)n) : nullptr;
+    double* du = sc.inout(u, (size_t)n);
+    double* dm = sc.inout(m, (size_t)n);
+    double* dv = sc.inout(v, (size_t)n);
+    double* dl = loss_hist ? sc.out(loss_hist, nsteps) : nullptr;
+    double* dk = kl_hist ? sc.out(kl_hist, nsteps) : nullptr;
+    double* c = sc.alloc<double>((size_t)n);
+    double* g = sc.alloc<double>((size_t)n, true);
+    double* ek = sc.alloc<double>(2);
+    int* dstep = sc.alloc<int>(1, true);
+    if (!sc.ok) return sc.finish();
+    const int tb = 256;
+    const unsigned gb = (unsigned)((n + tb - 1) / tb);
     {
-        Scope sc(h);
-        const double* dX = sc.in(X, (size_t)B * (d + 1));
-        const double* dY = sc.in(Y, (size_t)B * ycols);
-        const double* dlr = sc.in(lr_t, nsteps);
-        const unsigned char* dmask = mask ? sc.in(mask, (size_t)n) : nullptr;
-        double* du = sc.inout(u, (size_t)n);
-        double* dm = sc.inout(m, (size_t)n);
-        double* dv = sc.inout(v, (size_t)n);
-        double* dl = loss_hist ? sc.out(loss_hist, nsteps) : nullptr;
-        double* dk = kl_hist ? sc.out(kl_hist, nsteps) : nullptr;
-        double* c = sc.alloc<double>((size_t)n);
-        double* g = sc.alloc<double>((size_t)n, true);
-        double* ek = sc.alloc<double>(2);
-        if (!sc.ok) return sc.finish();
-        const int tb = 256;
-        const unsigned gb = (unsigned)((n + tb - 1) / tb);
-        const int was_async = h->async;
-        h->async = 1;  // the nested evaluations only enqueue: all their pointers are device memory
-        h->lik_var_dev = c + o_lv;
-        int* dstep = sc.alloc<int>(1, true);
-        if (!sc.ok) return sc.finish();
+        AsyncGuard guard(h);  // the nested evaluations only enqueue: all their pointers are device memory
         auto one_step = [&]() -> int {
-            svgp_constrain_kernel<<<gb, tb, 0, s>>>(du, c, n, n_theta);
-            int r = mfgp_svgp_elbo_grad(h, cfg, dX, dY, c + o_Z, c, has_W ? c + o_W : nullptr, c + o_qm, c + o_qs, 0.0, ek, ek + 1,
-                                        g + o_Z, g, has_W ? g + o_W : nullptr, g + o_qm, g + o_qs, g + o_lv);
-            svgp_adam_kernel<<<gb, tb, 0, s>>>(du, dm, dv, c, g, dmask, n, n_theta, dlr, dstep, beta1, beta2, eps, ek, cfg->kl_mult, dl, dk);
+            svgp_constrain_kernel<<<gb, tb, 0, s>>>(du, c, n, n_theta, o_lv, cfg->lik_lower);
+            int r = mfgp_svgp_elbo_grad_v(h, cfg, dX, dY, c + o_Z, c, has_W ? c + o_W : nullptr, c + o_qm, c + o_qs, c + o_lv, ek,
+                                          ek + 1, g + o_Z, g, has_W ? g + o_W : nullptr, g + o_qm, g + o_qs, g + o_lv);
+            svgp_adam_kernel<<<gb, tb, 0, s>>>(du, dm, dv, c, g, dmask, n, n_theta, o_lv, cfg->lik_lower, dlr, dstep, beta1, beta2,
+                                               eps, ek, cfg->kl_mult, dl, dk);
             svgp_step_inc_kernel<<<1, 1, 0, s>>>(dstep);
             return r;
         };
@@ -685,9 +754,75 @@ extern "C" int mfgp_svgp_adam(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const do
             if (graph) cudaGraphDestroy(graph);
         }
         for (; done < nsteps && rc == 0; ++done) rc = one_step();
-        h->lik_var_dev = nullptr;
-        h->async = was_async;
-        if (rc) return rc;
-        return sc.finish();
     }
+    if (rc) return rc;
+    return sc.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Building blocks of the DATA-PARALLEL device loop (reference loops singlebin_svgp.py:79-85,
+// linear_svgp.py:181-190): rows of the minibatch shard across ranks, every rank runs
+//     mfgp_svgp_constrain -> mfgp_svgp_elbo_grad_flat -> [all-reduce(sum) of eg, in place, by the caller] -> mfgp_svgp_adam_update
+// on device memory only; nothing is staged through the host and none of the three calls synchronises.
+extern "C" long mfgp_svgp_flat_size(const mfgp_svgp_cfg* cfg, int has_W) { return cfg ? FlatLayout(cfg, has_W).n : -1; }
+
+static int svgp_dp_check(mfgp_handle* h, const mfgp_svgp_cfg* cfg, int has_W, const char* who) {
+    if (!cfg) return mfgp_fail(h, MFGP_ERR_ARG, "%s: NULL cfg", who);
+    if (cfg->L < 1 || cfg->M < 1 || cfg->P < 1 || cfg->B < 1 || cfg->d < 1 || cfg->d > MFGP_MAX_D || (!has_W && cfg->L != cfg->P))
+        return mfgp_fail(h, MFGP_ERR_ARG, "%s: bad configuration", who);
+    return 0;
+}
+
+extern "C" int mfgp_svgp_constrain(mfgp_handle* h, const mfgp_svgp_cfg* cfg, int has_W, const double* u, double* c) {
+    if (!h) return MFGP_ERR_ARG;
+    MFGP_TRY(svgp_dp_check(h, cfg, has_W, "mfgp_svgp_constrain"));
+    if (!u || !c || !mfgp_is_device_ptr(u) || !mfgp_is_device_ptr(c))
+        return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_svgp_constrain: u and c must be device pointers");
+    cudaSetDevice(h->device);
+    const FlatLayout f(cfg, has_W);
+    svgp_constrain_kernel<<<(unsigned)((f.n + 255) / 256), 256, 0, h->stream>>>(u, c, f.n, f.n_theta, f.o_lv, cfg->lik_lower);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mfgp_svgp_elbo_grad_flat(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const double* X, const double* Y, int has_W,
+                                        const double* c, int nranks, double* eg) {
+    if (!h) return MFGP_ERR_ARG;
+    MFGP_TRY(svgp_dp_check(h, cfg, has_W, "mfgp_svgp_elbo_grad_flat"));
+    if (!X || !Y || !c || !eg || nranks < 1 || !mfgp_is_device_ptr(X) || !mfgp_is_device_ptr(Y) || !mfgp_is_device_ptr(c) ||
+        !mfgp_is_device_ptr(eg))
+        return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_svgp_elbo_grad_flat: X, Y, c, eg must be device pointers, nranks >= 1");
+    const FlatLayout f(cfg, has_W);
+    mfgp_svgp_cfg local = *cfg;
+    local.kl_mult = cfg->kl_mult / nranks;  // sum over ranks of (-scale VE_r + kl_mult / nranks KL) = -scale VE + kl_mult KL
+    double* g = eg + 2;
+    int rc;
+    {
+        AsyncGuard guard(h);
+        rc = mfgp_svgp_elbo_grad_v(h, &local, X, Y, c + f.o_Z, c, has_W ? c + f.o_W : nullptr, c + f.o_qm, c + f.o_qs, c + f.o_lv,
+                                   eg, eg + 1, g + f.o_Z, g, has_W ? g + f.o_W : nullptr, g + f.o_qm, g + f.o_qs, g + f.o_lv);
+    }
+    if (rc) return rc;
+    svgp_dp_fix_kernel<<<1, 1, 0, h->stream>>>(eg, 1.0 / nranks);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mfgp_svgp_adam_update(mfgp_handle* h, const mfgp_svgp_cfg* cfg, int has_W, double* u, double* m, double* v,
+                                     const unsigned char* mask, const double* c, const double* eg, const double* lr_t, int* step,
+                                     double beta1, double beta2, double eps, double* loss_hist, double* kl_hist, double* scratch2) {
+    if (!h) return MFGP_ERR_ARG;
+    MFGP_TRY(svgp_dp_check(h, cfg, has_W, "mfgp_svgp_adam_update"));
+    if (!u || !m || !v || !c || !eg || !lr_t || !step || !scratch2)
+        return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_svgp_adam_update: NULL argument");
+    cudaSetDevice(h->device);
+    const FlatLayout f(cfg, has_W);
+    cudaStream_t s = h->stream;
+    svgp_dp_hist_kernel<<<1, 1, 0, s>>>(eg, scratch2);
+    svgp_adam_kernel<<<(unsigned)((f.n + 255) / 256), 256, 0, s>>>(u, m, v, c, eg + 2, mask, f.n, f.n_theta, f.o_lv, cfg->lik_lower,
+                                                                  lr_t, step, beta1, beta2, eps, scratch2, cfg->kl_mult, loss_hist,
+                                                                  kl_hist);
+    svgp_step_inc_kernel<<<1, 1, 0, s>>>(step);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
 }

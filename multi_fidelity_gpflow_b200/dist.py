@@ -5,7 +5,10 @@ CPU tests).  How each sub-path shards:
   (`shard_range`, `gather_bins` only to assemble the result vector);
 * SVGP minibatch ELBO          -> rows of (X, Y) shard across ranks; every rank evaluates its rows
   with the global scale and kl_mult / world, then ONE all-reduce(sum) of the flat
-  [loss, kl, gradients] vector (`dp_svgp_value_and_grad`).
+  [loss, kl, gradients] vector.  `dp_svgp_adam` is the training loop: parameters, Adam moments and the
+  flat gradient stay in device memory, the kernels write the gradient pieces straight into the buffer
+  NCCL reduces in place, and the host never synchronises inside the loop.  `dp_svgp_value_and_grad` is
+  the one-evaluation form for host-driven optimisers (L-BFGS).
 """
 from __future__ import annotations
 
@@ -75,3 +78,118 @@ def dp_svgp_value_and_grad(local_fn, X, Y, num_data, kl_mult=1.0, group=None):
         if k.startswith("g_") and r[k] is None:
             out[k] = None
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Data-parallel SVGP training loop on device memory
+# ------------------------------------------------------------------------------------------------
+class SvgpDeviceOps:
+    """The three per-step calls of the data-parallel loop through the C-ABI (include/mfgp.h) on torch CUDA tensors.
+    The CPU schedule test (tests/test_host_logic.py) substitutes a double with the same three methods."""
+
+    def __init__(self, handle):
+        import torch
+
+        from . import _lib
+
+        self.torch, self._lib, self.h, self.L = torch, _lib, handle, _lib._lib
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def begin(self):
+        self.h.set_stream(self.torch.cuda.current_stream().cuda_stream)  # NCCL's stream: the three calls and the all-reduce are ordered
+        self.h.set_async(True)
+
+    def end(self):
+        self.torch.cuda.current_stream().synchronize()
+        self.h.set_async(False)
+        info = self.h.sync()
+        self.h.set_stream(None)
+        if info:
+            raise self._lib.NotPositiveDefiniteError(f"data-parallel SVGP: Cholesky of Kuu failed (pivot {info})")
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise self._lib.MFGPError(f"{what}: rc={rc}: {self.L.mfgp_last_error(self.h._h).decode()}")
+
+    def make_cfg(self, L, M, P, B, d, hetero, scale, kl_mult, lik_lower, masked, lik_per_output, jitter=1e-6):
+        return self._lib.SvgpCfg(L, M, P, B, d, int(hetero), float(scale), float(kl_mult), float(jitter), float(lik_lower),
+                                 int(masked), int(lik_per_output))
+
+    def constrain(self, cfg, has_W, u, c):
+        import ctypes as C
+
+        p = self._lib._ptr
+        self._chk(self.L.mfgp_svgp_constrain(self.h._h, C.byref(cfg), int(has_W), p(u), p(c)), "mfgp_svgp_constrain")
+
+    def elbo_grad_flat(self, cfg, X, Y, has_W, c, nranks, eg):
+        import ctypes as C
+
+        p = self._lib._ptr
+        self._chk(self.L.mfgp_svgp_elbo_grad_flat(self.h._h, C.byref(cfg), p(X), p(Y), int(has_W), p(c), int(nranks), p(eg)),
+                  "mfgp_svgp_elbo_grad_flat")
+
+    def adam_update(self, cfg, has_W, u, m, v, mask, c, eg, lr_t, step, b1, b2, eps, loss_hist, kl_hist, scratch):
+        import ctypes as C
+
+        p = self._lib._ptr
+        self._chk(self.L.mfgp_svgp_adam_update(self.h._h, C.byref(cfg), int(has_W), p(u), p(m), p(v), p(mask), p(c), p(eg), p(lr_t),
+                                               p(step), float(b1), float(b2), float(eps), p(loss_hist), p(kl_hist), p(scratch)),
+                  "mfgp_svgp_adam_update")
+
+
+def dp_svgp_adam(handle_or_ops, X, Y, shape, u, mask, lr_t, beta1, beta2, eps=1e-7, num_data=None, kl_mult=1.0,
+                 group=None, timing=None):
+    """len(lr_t) data-parallel Adam steps.  Every rank passes the same GLOBAL (mini)batch X [B, d+1], Y, the same flat
+    unconstrained parameter vector `u` (layout of mfgp_svgp_adam), trainable mask and per-step factors `lr_t`
+    (optimizers.adam_step_factors); rank r evaluates rows shard_range(B, r, world).
+
+    shape: dict(L, M, P, d, has_W, hetero, masked, lik_per_output, lik_lower).
+    Returns (u_final, loss_hist, kl_hist) as NumPy arrays, identical on every rank (same reduced gradient, same update).
+    timing (optional dict): receives 'ms_per_step' measured with device events around the loop (max over ranks is the
+    caller's job)."""
+    import torch
+
+    dist = _dist()
+    ops = handle_or_ops if hasattr(handle_or_ops, "elbo_grad_flat") else SvgpDeviceOps(handle_or_ops)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = ops.device
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    B, d = X.shape[0], X.shape[1] - 1
+    if B < world:
+        raise ValueError(f"batch of {B} rows cannot be sharded over {world} ranks")
+    lo, hi = shard_range(B, rank, world)
+    scale = float(num_data) / B if num_data is not None else 1.0
+    cfg = ops.make_cfg(shape["L"], shape["M"], shape["P"], hi - lo, d, shape.get("hetero", False), scale, kl_mult,
+                       shape.get("lik_lower", 1e-6), shape.get("masked", False), shape.get("lik_per_output", False))
+    has_W = bool(shape["has_W"])
+    n, nsteps = int(np.size(u)), int(len(lr_t))
+    f64 = dict(dtype=torch.float64, device=dev)
+    Xd, Yd = torch.from_numpy(X[lo:hi].copy()).to(dev), torch.from_numpy(Y[lo:hi].copy()).to(dev)
+    ud = torch.from_numpy(np.ascontiguousarray(u, dtype=np.float64).ravel().copy()).to(dev)
+    md, vd, c = torch.zeros(n, **f64), torch.zeros(n, **f64), torch.empty(n, **f64)
+    eg = torch.zeros(n + 2, **f64)
+    mk = None if mask is None else torch.from_numpy(np.ascontiguousarray(mask, dtype=np.uint8)).to(dev)
+    lrd = torch.from_numpy(np.ascontiguousarray(lr_t, dtype=np.float64)).to(dev)
+    step = torch.zeros(1, dtype=torch.int32, device=dev)
+    loss_h, kl_h, scratch = torch.zeros(nsteps, **f64), torch.zeros(nsteps, **f64), torch.zeros(2, **f64)
+    if hasattr(ops, "begin"):
+        ops.begin()
+    use_events = timing is not None and dev.type == "cuda"
+    if use_events:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier(group=group)
+        e0.record()
+    for _ in range(nsteps):
+        ops.constrain(cfg, has_W, ud, c)
+        ops.elbo_grad_flat(cfg, Xd, Yd, has_W, c, world, eg)
+        if world > 1:
+            dist.all_reduce(eg, op=dist.ReduceOp.SUM, group=group)  # in place on the buffer the kernels wrote
+        ops.adam_update(cfg, has_W, ud, md, vd, mk, c, eg, lrd, step, beta1, beta2, eps, loss_h, kl_h, scratch)
+    if use_events:
+        e1.record()
+    if hasattr(ops, "end"):
+        ops.end()
+    if use_events:
+        timing["ms_per_step"] = e0.elapsed_time(e1) / max(nsteps, 1)
+    return ud.cpu().numpy(), loss_h.cpu().numpy(), kl_h.cpu().numpy()

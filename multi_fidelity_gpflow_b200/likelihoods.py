@@ -13,6 +13,7 @@ DEFAULT_VARIANCE_LOWER_BOUND = 1e-6  # gpflow.likelihoods.Gaussian
 class Gaussian:
     _param_order = ("variance",)
     heteroscedastic = False
+    masked = False
 
     def __init__(self, variance=1.0):
         self.variance = Parameter(variance, transform=positive(lower=DEFAULT_VARIANCE_LOWER_BOUND))
@@ -26,3 +27,15 @@ class HeteroscedasticGaussian(Gaussian):
 
     def __init__(self, variance):
         self.variance = Parameter(np.asarray(variance, dtype=np.float64), transform=positive())  # linear_svgp.py:240
+
+
+class MaskedGaussian(Gaussian):
+    """Gaussian likelihood that ignores the NaN entries of Y (missing outputs) in the variational expectations, with one
+    trainable variance per output: reference notebooks/"demo: missing output.ipynb" cell 2 (class MaskedGaussian, built
+    with variance=np.ones(P)).  Like every likelihood here it only holds parameters; the masking is the `masked` epilogue
+    of the CUDA kernel (csrc/svgp.cu: mix_ve_kernel)."""
+
+    masked = True
+
+    def __init__(self, variance):
+        super().__init__(np.atleast_1d(np.asarray(variance, dtype=np.float64)))

@@ -7,7 +7,7 @@ import numpy as np
 
 from .base import Parameter
 from .kernels import LinearCoregionalization, replicate_mf_kernels
-from .likelihoods import Gaussian, HeteroscedasticGaussian
+from .likelihoods import Gaussian, HeteroscedasticGaussian, MaskedGaussian
 from .optimizers import Adam, CosineDecay
 from .svgp_base import SVGPBase, kmeans_inducing_points
 
@@ -36,7 +36,7 @@ def initialize_W_pca(Y, output_dim, num_latents, perturb=0.01):
 class LatentMFCoregionalizationSVGP(SVGPBase):
     def __init__(self, X, Y, kernel_L, kernel_delta, num_latents, num_inducing=None, num_outputs=None, use_rho=True,
                  heterosed=False, loss_type="gaussian", w_type="diagonal", window_fraction=0.4, scale=0.2, Z=None,
-                 q_sqrt_scale=1.0, handle=None):
+                 q_sqrt_scale=1.0, handle=None, masked=False):
         X = np.asarray(X, dtype=np.float64)
         Y = np.asarray(Y, dtype=np.float64)
         if num_outputs is None:
@@ -57,7 +57,13 @@ class LatentMFCoregionalizationSVGP(SVGPBase):
         kernel = LinearCoregionalization(replicate_mf_kernels(kernel_L, kernel_delta, num_latents, use_rho, handle), W=W)
         Z_init = kmeans_inducing_points(X, num_inducing, 42)  # :125-126
         variance = np.array([1.0])
-        if heterosed:
+        if masked:
+            # the MaskedGaussian of notebooks/"demo: missing output.ipynb" (NaN = missing output, one
+            # variance per output) on the multi-fidelity latent model; not a constructor option of the reference class
+            if heterosed:
+                raise ValueError("masked and heterosed likelihoods are exclusive")
+            likelihood = MaskedGaussian(variance=np.ones(num_outputs))
+        elif heterosed:
             if loss_type != "gaussian":
                 raise NotImplementedError("HeteroscedasticPoisson is marked NOT FULLY IMPLEMENTED in the reference (:288)")
             likelihood = HeteroscedasticGaussian(variance=variance)

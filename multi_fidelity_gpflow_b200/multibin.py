@@ -42,6 +42,7 @@ class MultiBinMFGP:
         self.v = np.zeros_like(self.u)
         self.iterations = 0
         self.loss_history = np.zeros((0, self.R, self.P))
+        self.failed = np.zeros((self.R, self.P), dtype=np.int32)  # first failing Cholesky pivot per (restart, bin), 0 = healthy
 
     # ---- parameters --------------------------------------------------------------------------------
     @property
@@ -50,17 +51,22 @@ class MultiBinMFGP:
         return self._tf.forward(self.u).reshape(self.R, self.P, -1)
 
     def training_loss(self):
-        """NLML of every (restart, bin): [R, P]."""
+        """NLML of every (restart, bin): [R, P]; NaN where that problem's covariance is not positive definite."""
         B = self.R * self.P
+        info = np.zeros(B, dtype=np.int32)
         nlml, _ = self.handle.gpr_batched_nlml_grad(self.X, self.Y, self.thetas.reshape(B, -1), np.full(B, self.noise),
-                                                    want_grad=False)
-        return nlml.reshape(self.R, self.P)
+                                                    info=info, want_grad=False)
+        return np.where(info == 0, nlml, np.nan).reshape(self.R, self.P)
 
     def log_marginal_likelihood(self):
         return -self.training_loss()
 
     # ---- training ------------------------------------------------------------------------------------
     def optimize(self, max_iters=1000, learning_rate=0.01, use_cosine_decay=False, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        """max_iters Adam steps for all R * P problems on the device.  A restart whose covariance stops being positive
+        definite is that restart's failure only: `failed[r, p]` records the 1-based pivot of its first failure, its later
+        losses are NaN (so best_restart() skips it) and the remaining restarts train on -- the step counter and
+        loss_history advance for everyone, so the bias correction / schedule stay right on the next call."""
         lr_t, b1, b2 = adam_step_factors(learning_rate, max_iters, first_step=self.iterations,
                                          cosine_decay_steps=max_iters if use_cosine_decay else None, beta_1=beta_1, beta_2=beta_2)
         B = self.R * self.P
@@ -70,6 +76,8 @@ class MultiBinMFGP:
                                      fix_rho=not self.use_rho, loss_hist=hist, info=info)
         self.iterations += max_iters
         self.loss_history = np.concatenate([self.loss_history, hist.reshape(max_iters, self.R, self.P)])
+        new = info.reshape(self.R, self.P)
+        self.failed = np.where(self.failed != 0, self.failed, new)
         return self
 
     # ---- model selection and prediction ----------------------------------------------------------------

@@ -64,7 +64,9 @@ class SVGPBase:
         return None if W is None else W.numpy()
 
     def _lik_var(self):
-        return float(np.ravel(self.likelihood.variance.numpy())[0])
+        """Scalar, or the [P] vector of a per-output likelihood (MaskedGaussian)."""
+        v = np.ravel(self.likelihood.variance.numpy())
+        return float(v[0]) if v.size == 1 else v
 
     @property
     def trainable_variables(self):
@@ -88,6 +90,7 @@ class SVGPBase:
         return self.handle.svgp_elbo_grad(
             X, Y, self.Z.numpy(), self._thetas(d), self._W(), self.q_mu.numpy(), np.tril(self.q_sqrt.numpy()),
             self._lik_var(), scale=scale, kl_mult=kl_multiplier, hetero=self.likelihood.heteroscedastic, want_grad=want_grad,
+            masked=self.likelihood.masked,
         ), d
 
     def elbo(self, data):
@@ -114,7 +117,8 @@ class SVGPBase:
             for p, gu in k.scatter_theta_grad(r["g_thetas"][l], d):
                 by[id(p)] = gu
         lv = self.likelihood.variance
-        by[id(lv)] = lv.grad_to_unconstrained(np.full(lv.shape, r["g_lik_var"]) if lv.shape else r["g_lik_var"])
+        g_lv = r["g_lik_var"]
+        by[id(lv)] = lv.grad_to_unconstrained(g_lv if np.ndim(g_lv) else (np.full(lv.shape, g_lv) if lv.shape else g_lv))
         loss = -r["elbo"] + (kl_multiplier - 1.0) * r["kl"]
         return loss, r["kl"], [np.asarray(by[id(p)], dtype=np.float64).reshape(p.shape) for p in variables]
 
@@ -137,16 +141,7 @@ class SVGPBase:
             o += cnt
         return items, o
 
-    def optimize_on_device(self, data, max_iters, initial_lr, kl_multiplier=1.0):
-        """The model's optimize() loop -- full-batch Adam with CosineDecay(initial_lr, max_iters) on the unconstrained
-        trainable variables, loss = -ELBO + (kl_multiplier - 1) KL -- run by mfgp_svgp_adam without a host round trip per
-        step.  Same trajectory as optimize() (tests/test_svgp_device_loop.py); appends to loss_history / kl_history."""
-        from .optimizers import adam_step_factors
-
-        X, Y = data
-        X = np.ascontiguousarray(X, dtype=np.float64)
-        Y = np.ascontiguousarray(Y, dtype=np.float64)
-        d = X.shape[1] - 1
+    def _flat_pack(self, d):
         items, n = self._flat_parameters(d)
         u, mask = np.empty(n), np.zeros(n, dtype=np.uint8)
         for par, sl in items:
@@ -155,20 +150,69 @@ class SVGPBase:
                 vals = np.ravel(np.tril(par.unconstrained))
             u[sl] = vals
             mask[sl] = 1 if par.trainable else 0
-        lr_t, b1, b2 = adam_step_factors(initial_lr, int(max_iters), cosine_decay_steps=int(max_iters))
-        m, v = np.zeros(n), np.zeros(n)
+        return items, u, mask
+
+    def _device_loop(self, data, max_iters, initial_lr, kl_multiplier, run):
+        """Shared by optimize_on_device / optimize_data_parallel: history semantics of the reference loops, flat packing,
+        per-step factors; `run(X, Y, shape, u, mask, lr_t, b1, b2, scale)` -> (u_final, loss_hist, kl_hist)."""
+        from .optimizers import adam_step_factors
+
+        X, Y = data
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        d = X.shape[1] - 1
+        resumable = hasattr(self, "kl_history")
+        if not resumable:
+            self.loss_history = []
+        nsteps = int(max_iters) - (len(self.loss_history) if resumable else 0)
+        if nsteps <= 0:
+            return self
+        items, u, mask = self._flat_pack(d)
+        lr_t, b1, b2 = adam_step_factors(initial_lr, nsteps, cosine_decay_steps=int(max_iters))
         M, L = self.q_mu.shape
         W = getattr(self.kernel, "W", None)
-        P = L if W is None else W.shape[0]
-        scale = 1.0 if self.num_data is None else float(self.num_data) / X.shape[0]
-        loss, kl = self.handle.svgp_adam(X, Y, L, M, P, W is not None, u, m, v, mask, lr_t, b1, b2, 1e-7, scale=scale,
-                                         kl_mult=kl_multiplier, hetero=self.likelihood.heteroscedastic)
+        lik = self.likelihood
+        shape = dict(L=L, M=M, P=L if W is None else W.shape[0], d=d, has_W=W is not None, hetero=lik.heteroscedastic,
+                     masked=lik.masked, lik_per_output=int(np.size(lik.variance.unconstrained)) > 1,
+                     lik_lower=lik.variance.transform.lower)
+        u, loss, kl = run(X, Y, shape, u, mask, lr_t, b1, b2)
         for par, sl in items:
             par.unconstrained = u[sl].reshape(np.shape(par.unconstrained)).copy()
         self.loss_history = list(self.loss_history) + list(loss)
-        if hasattr(self, "kl_history"):
+        if resumable:
             self.kl_history = list(self.kl_history) + list(kl)
         return self
+
+    def optimize_on_device(self, data, max_iters, initial_lr, kl_multiplier=1.0):
+        """The model's optimize() loop -- full-batch Adam with CosineDecay(initial_lr, max_iters) on the unconstrained
+        trainable variables, loss = -ELBO + (kl_multiplier - 1) KL -- run by mfgp_svgp_adam without a host round trip per
+        step.  Same trajectory and the same history semantics as the model's optimize() (tests/test_svgp_device_loop.py):
+        a model with a `kl_history` (LatentMFCoregionalizationSVGP, linear_svgp.py:194) runs the REMAINING steps
+        range(len(loss_history), max_iters) and appends; SingleBinSVGP (singlebin_svgp.py:79) resets loss_history and runs
+        max_iters steps.  Like the reference, every call starts a fresh optimizer (Adam moments zero, iteration 0)."""
+
+        def run(X, Y, shape, u, mask, lr_t, b1, b2):
+            scale = 1.0 if self.num_data is None else float(self.num_data) / X.shape[0]
+            m, v = np.zeros_like(u), np.zeros_like(u)
+            loss, kl = self.handle.svgp_adam(X, Y, shape["L"], shape["M"], shape["P"], shape["has_W"], u, m, v, mask, lr_t, b1, b2,
+                                             1e-7, scale=scale, kl_mult=kl_multiplier, hetero=shape["hetero"],
+                                             lik_lower=shape["lik_lower"], masked=shape["masked"],
+                                             lik_per_output=shape["lik_per_output"])
+            return u, loss, kl
+
+        return self._device_loop(data, max_iters, initial_lr, kl_multiplier, run)
+
+    def optimize_data_parallel(self, data, max_iters, initial_lr, kl_multiplier=1.0, group=None, timing=None):
+        """optimize_on_device across the ranks of a torch.distributed group (one process per GPU, NCCL): the rows of the
+        batch shard across ranks, one in-place all-reduce of the flat device gradient per step (dist.dp_svgp_adam); every
+        rank ends with the same parameters and histories."""
+        from .dist import dp_svgp_adam
+
+        def run(X, Y, shape, u, mask, lr_t, b1, b2):
+            return dp_svgp_adam(self.handle, X, Y, shape, u, mask, lr_t, b1, b2, 1e-7, num_data=self.num_data,
+                                kl_mult=kl_multiplier, group=group, timing=timing)
+
+        return self._device_loop(data, max_iters, initial_lr, kl_multiplier, run)
 
     def predict_f(self, Xnew, full_cov=False, full_output_cov=False):
         if full_cov or full_output_cov:

@@ -145,6 +145,55 @@ def gpr_lml(X, Y, theta, noise):
     return float(np.sum(p))
 
 
+def gpr_lml_grad_analytic(X, Y, theta, noise):
+    """LML and its gradient w.r.t. the CONSTRAINED [theta (2d+3), noise] in closed form:
+    G = alpha alpha^T - P K_n^-1, dLML/dtheta = 1/2 sum_ij G_ij dK_ij/dtheta, dLML/dnoise = 1/2 tr G, with the kernel
+    derivatives of App. A.1 (mfgpflow/linear.py:93-102 differentiated by hand).  It is what tape.gradient (linear.py:207)
+    returns, without autograd's memory: the large-N parity cases (N > 12 288) use it; tests/test_oracle_fd.py checks it
+    against the torch-autograd twin and central finite differences at small N.  Returns (lml, g_theta, g_noise)."""
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    N, d, P = X.shape[0], X.shape[1] - 1, Y.shape[1]
+    rho, lsL, vL, lsD, vD = unpack_theta(theta, d)
+    f = X[:, -1]
+    s = np.where(f == 0, 1.0, np.where(f == 1, rho, 0.0))
+    hidx = np.where(f == 1)[0]
+    x = np.where(((f == 0) | (f == 1))[:, None], X[:, :-1], 0.0)
+    KL = se_K(x, x, lsL, vL)
+    K = KL * s[:, None]
+    K *= s[None, :]
+    xh = x[hidx]
+    KD = se_K(xh, xh, lsD, vD)
+    K[np.ix_(hidx, hidx)] += KD
+    K[np.diag_indices(N)] += noise
+    c = sla.cho_factor(K, lower=True, overwrite_a=True, check_finite=False)
+    alpha = sla.cho_solve(c, Y, check_finite=False)
+    lml = float(-0.5 * np.sum(Y * alpha) - P * (0.5 * N * LOG2PI + np.sum(np.log(np.diag(c[0])))))
+    G = sla.cho_solve(c, np.eye(N), check_finite=False)  # K_n^-1
+    del c, K
+    G *= -float(P)
+    G += alpha @ alpha.T
+    g = np.zeros(2 * d + 3)
+    g_noise = 0.5 * float(np.trace(G))
+    GD = G[np.ix_(hidx, hidx)] * KD  # discrepancy terms live on the HF x HF block only
+    KL *= G  # from here on KL holds G o K_L
+    # d(s_i s_j)/d rho = h_i s_j + s_i h_j
+    hs = np.zeros(N)
+    hs[hidx] = 1.0
+    g[0] = 0.5 * (2.0 * float(hs @ (KL @ s)))
+    KL *= s[:, None]
+    KL *= s[None, :]  # T^L = G o (s s^T) o K_L
+    g[1 + d] = 0.5 * float(KL.sum()) / vL
+    g[2 + 2 * d] = 0.5 * float(GD.sum()) / vD
+    rs, rsD = KL.sum(axis=1), GD.sum(axis=1)
+    for k in range(d):
+        # sum_ij T_ij (x_i - x_j)^2 = 2 sum_i rowsum_i x_i^2 - 2 x^T T x   (T symmetric)
+        xk, xhk = x[:, k], xh[:, k]
+        g[1 + k] = 0.5 * (2.0 * float(rs @ (xk * xk)) - 2.0 * float(xk @ (KL @ xk))) / lsL[k] ** 3
+        g[2 + d + k] = 0.5 * (2.0 * float(rsD @ (xhk * xhk)) - 2.0 * float(xhk @ (GD @ xhk))) / lsD[k] ** 3
+    return lml, g, g_noise
+
+
 def gpr_predict(X, Y, Xnew, theta, noise):
     """GPR.predict_f(full_cov=False): base_conditional(white=False).  var is [N*] (same for every column)."""
     X = np.asarray(X, dtype=np.float64)
@@ -225,11 +274,24 @@ def gaussian_var_exp(Y, f_mean, f_var, lik_var, hetero=False):
     return np.sum(ve, axis=-1)
 
 
-def svgp_elbo(Xb, Yb, Z, thetas, q_mu, q_sqrt, lik_var, W=None, num_data=None, hetero=False):
+def masked_gaussian_var_exp(Y, f_mean, f_var, lik_var):
+    """MaskedGaussian._variational_expectations (reference notebooks/"demo: missing output.ipynb", cell 2): NaN entries of Y
+    are missing outputs.  Follows the cell line by line: mask = ~isnan(Y); Y, Fmu, Fvar filled with 0 where masked; the
+    closed-form Gaussian VE with the (per-output, shape [P]) variance; masked entries set to 0; sum over outputs -> [B]."""
+    mask = ~np.isnan(Y)
+    Yf = np.where(mask, Y, 0.0)
+    Fm = np.where(mask, f_mean, 0.0)
+    Fv = np.where(mask, f_var, 0.0)
+    var = np.asarray(lik_var, dtype=np.float64)
+    ve = -0.5 * np.log(2.0 * np.pi) - 0.5 * np.log(var) - 0.5 * ((Yf - Fm) ** 2 + Fv) / var
+    return np.sum(np.where(mask, ve, 0.0), axis=-1)
+
+
+def svgp_elbo(Xb, Yb, Z, thetas, q_mu, q_sqrt, lik_var, W=None, num_data=None, hetero=False, masked=False):
     """SVGP.elbo((X, Y)).  Returns (elbo, kl)."""
     kl = prior_kl(q_mu, q_sqrt)
     f_mean, f_var = svgp_predict(Xb, Z, thetas, q_mu, q_sqrt, W)
-    ve = gaussian_var_exp(Yb, f_mean, f_var, lik_var, hetero)
+    ve = masked_gaussian_var_exp(Yb, f_mean, f_var, lik_var) if masked else gaussian_var_exp(Yb, f_mean, f_var, lik_var, hetero)
     scale = 1.0 if num_data is None else float(num_data) / Xb.shape[0]
     return float(np.sum(ve) * scale - kl), kl
 

@@ -5,8 +5,8 @@ TEST INFRASTRUCTURE ONLY (same rule as mfgp_oracle.py: never imported by the pro
 The reference obtains gradients with ``tf.GradientTape`` through the graph restated in
 ``mfgp_oracle.py`` (``linear.py:205-207``, ``singlebin_svgp.py:82-84``,
 ``linear_svgp.py:183-189``).  This file builds the same graph in torch so reverse-mode
-autodiff yields the same derivative; tests additionally check it against central finite
-differences of the NumPy forward.  It is also the "port" CPU baseline timed by bench.py
+autodiff yields the same derivative; tests/test_oracle_fd.py checks it against central finite
+differences of the NumPy forward (every parameter group, every likelihood variant).  It is also the "port" CPU baseline timed by bench.py
 (all host threads), because the reference's TensorFlow/GPflow cannot be installed here.
 """
 from __future__ import annotations
@@ -129,11 +129,19 @@ def svgp_predict(Xb, Z, thetas, q_mu, q_sqrt, W=None):
     return g_mean @ W.T, g_var @ (W * W).T
 
 
-def svgp_elbo(Xb, Yb, Z, thetas, q_mu, q_sqrt, lik_var, W=None, num_data=None, hetero=False):
+def svgp_elbo(Xb, Yb, Z, thetas, q_mu, q_sqrt, lik_var, W=None, num_data=None, hetero=False, masked=False):
     Xb, Yb = _t(Xb), _t(Yb)
     kl = prior_kl(q_mu, q_sqrt)
     f_mean, f_var = svgp_predict(Xb, Z, thetas, q_mu, q_sqrt, W)
     P = f_mean.shape[1]
+    if masked:  # MaskedGaussian (notebooks/"demo: missing output.ipynb" cell 2): tf.where fills, then zeroes the masked VE
+        mask = ~torch.isnan(Yb)
+        zero = torch.zeros_like(f_mean)
+        Yf, Fm, Fv = torch.where(mask, Yb, zero), torch.where(mask, f_mean, zero), torch.where(mask, f_var, zero)
+        ve = -0.5 * LOG2PI - 0.5 * torch.log(lik_var) - 0.5 * ((Yf - Fm) ** 2 + Fv) / lik_var
+        ve = torch.where(mask, ve, zero)
+        scale = 1.0 if num_data is None else float(num_data) / Xb.shape[0]
+        return ve.sum() * scale - kl, kl
     if hetero:
         Yo, Yu = Yb[:, :P], Yb[:, P:]
         ev = lik_var + Yu * Yu
@@ -145,7 +153,8 @@ def svgp_elbo(Xb, Yb, Z, thetas, q_mu, q_sqrt, lik_var, W=None, num_data=None, h
     return ve.sum() * scale - kl, kl
 
 
-def svgp_value_and_grad(Xb, Yb, Z, thetas, q_mu, q_sqrt, lik_var, W=None, num_data=None, hetero=False, kl_mult=1.0):
+def svgp_value_and_grad(Xb, Yb, Z, thetas, q_mu, q_sqrt, lik_var, W=None, num_data=None, hetero=False, kl_mult=1.0,
+                        masked=False):
     """loss = -ELBO + (kl_mult-1)*KL (linear_svgp.py:188).  Gradients w.r.t. CONSTRAINED values.
 
     Returns dict(loss, elbo, kl, g_Z, g_thetas, g_q_mu, g_q_sqrt, g_W, g_lik_var).
@@ -154,13 +163,14 @@ def svgp_value_and_grad(Xb, Yb, Z, thetas, q_mu, q_sqrt, lik_var, W=None, num_da
     tth = torch.tensor(np.asarray(thetas, dtype=np.float64), requires_grad=True)
     tqm = torch.tensor(np.asarray(q_mu, dtype=np.float64), requires_grad=True)
     tqs = torch.tensor(np.asarray(q_sqrt, dtype=np.float64), requires_grad=True)
-    tlv = torch.tensor(np.asarray(lik_var, dtype=np.float64).reshape(()), requires_grad=True)
+    lv = np.asarray(lik_var, dtype=np.float64)
+    tlv = torch.tensor(lv.reshape(()) if lv.size == 1 else lv.ravel(), requires_grad=True)  # [P] vector: MaskedGaussian
     leaves = [tz, tth, tqm, tqs, tlv]
     tw = None
     if W is not None:
         tw = torch.tensor(np.asarray(W, dtype=np.float64), requires_grad=True)
         leaves.append(tw)
-    elbo, kl = svgp_elbo(Xb, Yb, tz, tth, tqm, tqs, tlv, tw, num_data, hetero)
+    elbo, kl = svgp_elbo(Xb, Yb, tz, tth, tqm, tqs, tlv, tw, num_data, hetero, masked)
     loss = -elbo + (kl_mult - 1.0) * kl
     gs = torch.autograd.grad(loss, leaves)
     out = dict(
@@ -171,7 +181,7 @@ def svgp_value_and_grad(Xb, Yb, Z, thetas, q_mu, q_sqrt, lik_var, W=None, num_da
         g_thetas=gs[1].numpy().copy(),
         g_q_mu=gs[2].numpy().copy(),
         g_q_sqrt=np.tril(gs[3].numpy()).copy(),
-        g_lik_var=float(gs[4]),
+        g_lik_var=float(gs[4]) if lv.size == 1 else gs[4].numpy().copy(),
         g_W=None if W is None else gs[5].numpy().copy(),
     )
     return out

@@ -118,6 +118,44 @@ def test_potrf_and_inverse(h, N):
     np.testing.assert_allclose(W[:, :N] @ Lr, np.eye(N), atol=1e-8)
 
 
+def test_potrf_and_inverse_large_outer_block_512(h):
+    """N = 13 000 is just past the switch to rank-512 trailing updates (csrc/chol.cu, N > 12 288) and exercises the
+    look-ahead / priority-stream chain that bench.py times at N = 16 384; checked against LAPACK."""
+    N = 13000
+    ds = onp.synthetic_exact_dataset(N)
+    K = onp.mf_K(ds["X"], None, ds["theta"])
+    K[np.diag_indices(N)] += ds["noise"]
+    Lr = np.linalg.cholesky(K)
+    A = np.tril(K)
+    del K
+    L, W = h.potrf(A, want_inverse=True)
+    del A
+    # conditioning ~1e3 N: compare in the backward-error sense the factorisation guarantees
+    scale = np.abs(Lr).max()
+    assert np.abs(L - Lr).max() < 1e-10 * scale
+    assert np.all(np.triu(L[:256, :256], 1) == 0)
+    # W = inv(L): check W L = I on a slab of rows (the full product would need a 13 000^3 CPU GEMM; 1/13 of it is enough
+    # to cover every merge level of the blocked trtri)
+    rows = np.r_[0:300, 6400:6700, N - 400:N]
+    R = W[rows] @ Lr
+    R[np.arange(rows.size), rows] -= 1.0
+    assert np.abs(R).max() < 1e-8
+
+
+@pytest.mark.parametrize("N", [4096, 13000])
+def test_gpr_nlml_grad_large_vs_oracle(h, N):
+    """Exact-GPR objective + gradient beyond the sizes of the datasets: N = 4096 (rank-256 path) and N = 13 000 (rank-512
+    path), C5 synthetic data, against the oracle's closed form (validated against autograd + finite differences in
+    tests/test_oracle_fd.py).  North-star tolerances: 1e-9 on the value, 1e-7 on the gradient."""
+    ds = onp.synthetic_exact_dataset(N)
+    nlml, g = h.gpr_nlml_grad(ds["X"], ds["Y"], ds["theta"], ds["noise"])
+    lml, gth, gnz = onp.gpr_lml_grad_analytic(ds["X"], ds["Y"], ds["theta"], ds["noise"])
+    assert abs(nlml + lml) < 1e-9 * abs(lml), (nlml, lml)
+    ref = -np.concatenate([gth, [gnz]])
+    np.testing.assert_allclose(g, ref, rtol=1e-7, atol=1e-7 * np.abs(ref).max())
+    assert abs(h.gpr_nlml(ds["X"], ds["Y"], ds["theta"], ds["noise"]) - nlml) < 1e-12 * abs(nlml)
+
+
 def test_potrf_not_positive_definite(h):
     from multi_fidelity_gpflow_b200._lib import NotPositiveDefiniteError
 

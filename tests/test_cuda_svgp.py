@@ -33,13 +33,13 @@ def make_problem(rng, X, Y, Z, L, d, mixing, hetero=False, perturb=True):
     return dict(X=X, Y=Yh, Z=Zp, thetas=th, q_mu=q_mu, q_sqrt=q_sqrt, W=W)
 
 
-def compare(h, pr, lik_var, num_data=None, kl_mult=1.0, hetero=False, vtol=1e-9, gtol=1e-7):
+def compare(h, pr, lik_var, num_data=None, kl_mult=1.0, hetero=False, vtol=1e-9, gtol=1e-7, masked=False):
     B = pr["X"].shape[0]
     scale = 1.0 if num_data is None else num_data / B
     got = h.svgp_elbo_grad(pr["X"], pr["Y"], pr["Z"], pr["thetas"], pr["W"], pr["q_mu"], pr["q_sqrt"], lik_var,
-                           scale=scale, kl_mult=kl_mult, hetero=hetero)
+                           scale=scale, kl_mult=kl_mult, hetero=hetero, masked=masked)
     ref = otc.svgp_value_and_grad(pr["X"], pr["Y"], pr["Z"], pr["thetas"], pr["q_mu"], pr["q_sqrt"], lik_var, pr["W"],
-                                  num_data, hetero, kl_mult)
+                                  num_data, hetero, kl_mult, masked)
     assert abs(got["elbo"] - ref["elbo"]) <= vtol * abs(ref["elbo"]), (got["elbo"], ref["elbo"])
     assert abs(got["kl"] - ref["kl"]) <= vtol * max(1.0, abs(ref["kl"]))
     for k in ("g_q_mu", "g_q_sqrt", "g_Z", "g_thetas", "g_W"):
@@ -47,7 +47,7 @@ def compare(h, pr, lik_var, num_data=None, kl_mult=1.0, hetero=False, vtol=1e-9,
             continue
         scale_k = np.abs(ref[k]).max()
         np.testing.assert_allclose(got[k], ref[k], rtol=gtol, atol=gtol * max(scale_k, 1e-30), err_msg=k)
-    assert abs(got["g_lik_var"] - ref["g_lik_var"]) <= gtol * abs(ref["g_lik_var"])
+    np.testing.assert_allclose(got["g_lik_var"], ref["g_lik_var"], rtol=gtol, atol=gtol * np.abs(ref["g_lik_var"]).max())
     assert np.all(got["g_Z"][:, -1] == 0)  # quirk Q5: fidelity column of Z gets exactly zero gradient
     return got, ref
 
@@ -77,6 +77,29 @@ def test_hbs_latent_heteroscedastic(h):
     ds = onp.load_dataset("hbs")
     pr = make_problem(np.random.default_rng(3), ds["X"], ds["Y"], ds["Z_kmeans50"], 10, 5, True, hetero=True)
     compare(h, pr, 0.5, num_data=53, hetero=True)
+
+
+@pytest.mark.parametrize("mixing,L", [(True, 10), (False, 49)])
+def test_masked_gaussian_missing_outputs(h, mixing, L):
+    """MaskedGaussian (reference notebooks/"demo: missing output.ipynb" cell 2) -- NaN entries of Y are
+    missing outputs, one likelihood variance per output.  ~30 % of the entries missing, one output missing entirely."""
+    ds = onp.load_dataset("hbs")
+    rng = np.random.default_rng(11)
+    pr = make_problem(rng, ds["X"], ds["Y"], ds["Z_kmeans50"], L, 5, mixing)
+    Y = pr["Y"].copy()
+    Y[rng.random(Y.shape) < 0.3] = np.nan
+    Y[:, 7] = np.nan
+    pr["Y"] = Y
+    lik = 0.4 + rng.random(49)
+    got, ref = compare(h, pr, lik, num_data=53, masked=True)
+    assert got["g_lik_var"].shape == (49,) and got["g_lik_var"][7] == 0.0  # a never-observed output has no likelihood gradient
+    # no NaN in Y: the masked epilogue with equal variances is the plain Gaussian one
+    pr["Y"] = ds["Y"]
+    a = h.svgp_elbo_grad(pr["X"], pr["Y"], pr["Z"], pr["thetas"], pr["W"], pr["q_mu"], pr["q_sqrt"], np.full(49, 0.8), masked=True)
+    b = h.svgp_elbo_grad(pr["X"], pr["Y"], pr["Z"], pr["thetas"], pr["W"], pr["q_mu"], pr["q_sqrt"], 0.8)
+    assert a["elbo"] == b["elbo"]
+    np.testing.assert_allclose(a["g_lik_var"].sum(), b["g_lik_var"], rtol=1e-12)
+    np.testing.assert_array_equal(a["g_thetas"], b["g_thetas"])
 
 
 def test_minibatch_rows(h):

@@ -138,9 +138,33 @@ def _gloo_worker(rank, world, port, q):
         return otc.svgp_value_and_grad(Xr, Yr, Z, ths, q_mu, q_sqrt, 0.8, W, num_data=scale * Xr.shape[0], kl_mult=klm)
 
     out = dp_svgp_value_and_grad(local_fn, X, Y, num_data=53, kl_mult=1.7)
+    # (3) the data-parallel TRAINING loop (dist.dp_svgp_adam): flat buffers, in-place all-reduce, Adam on every rank;
+    #     block arithmetic by the oracle double, schedule / sharding / reduce convention by the product code
+    from multi_fidelity_gpflow_b200.dist import dp_svgp_adam
+    from multi_fidelity_gpflow_b200.optimizers import adam_step_factors
+    from tests._helpers import OracleSvgpOps
+
+    solo = dist.new_group([0])
+    u0, mask, shape = _dp_loop_problem(onp, X, Y, Z, ths, W, q_mu, q_sqrt)
+    lr_t, b1, b2 = adam_step_factors(0.05, 3, cosine_decay_steps=3)
+    res2 = dp_svgp_adam(OracleSvgpOps(), X, Y, shape, u0, mask, lr_t, b1, b2, num_data=53, kl_mult=1.7)
+    res1 = dp_svgp_adam(OracleSvgpOps(), X, Y, shape, u0, mask, lr_t, b1, b2, num_data=53, kl_mult=1.7, group=solo) if rank == 0 else None
     if rank == 0:
-        q.put((full_v, full_g, out))
+        q.put((full_v, full_g, out, res2, res1))
+    else:
+        q.put(("rank1", res2))
     dist.destroy_process_group()
+
+
+def _dp_loop_problem(onp, X, Y, Z, ths, W, q_mu, q_sqrt):
+    L, M, P, d = ths.shape[0], Z.shape[0], W.shape[0], X.shape[1] - 1
+    u0 = np.concatenate([onp.softplus_inv(ths).ravel(), Z.ravel(), W.ravel(), q_mu.ravel(), np.tril(q_sqrt).ravel(),
+                         onp.softplus_inv(np.array([0.8 - 1e-6]))])
+    mask = np.ones(u0.size, dtype=np.uint8)
+    mask[L * (2 * d + 3) + d::d + 1][:M] = 1  # (fidelity column trainable in name; its gradient is exactly zero, quirk Q5)
+    mask[0] = 0  # rho of latent 0 frozen: a masked entry must not move on any rank
+    shape = dict(L=L, M=M, P=P, d=d, has_W=True, hetero=False, masked=False, lik_per_output=False, lik_lower=1e-6)
+    return u0, mask, shape
 
 
 def test_two_rank_gloo_sharding_matches_single_process():
@@ -154,10 +178,19 @@ def test_two_rank_gloo_sharding_matches_single_process():
     procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    full_v, full_g, out = q.get(timeout=240)
+    got = [q.get(timeout=480), q.get(timeout=480)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    (full_v, full_g, out, res2, res1), = [g for g in got if len(g) == 5]
+    (_, res2_rank1), = [g for g in got if len(g) == 2]
+    # data-parallel loop: both ranks end bit-identical; two ranks follow the one-rank trajectory to rounding
+    for a, b in zip(res2, res2_rank1):
+        assert np.array_equal(a, b)
+    np.testing.assert_allclose(res2[0], res1[0], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(res2[1], res1[1], rtol=1e-11)
+    np.testing.assert_allclose(res2[2], res1[2], rtol=1e-11)
+    assert res2[1][-1] < res2[1][0] and res2[0][0] == res1[0][0]  # the loss went down; the frozen entry never moved
     ds = onp.load_dataset("hbs")
     X, Y = ds["X"], ds["Y"][:, :6]
     rng = np.random.default_rng(0)
@@ -228,16 +261,22 @@ class _FakeHandle:
 
     def __init__(self):
         self.calls = []
+        self.fail_problem = None  # flat index of a problem whose Cholesky "fails" (per-problem info, no exception)
 
-    def gpr_batched_nlml_grad(self, X, Y, thetas, noises, want_grad=True, **kw):
+    def gpr_batched_nlml_grad(self, X, Y, thetas, noises, want_grad=True, info=None, **kw):
         self.calls.append(("eval", thetas.shape, Y.shape))
         nlml = thetas[:, 0] * 10.0 + np.arange(thetas.shape[0]) % Y.shape[1]  # depends on rho and on the bin
+        if self.fail_problem is not None and info is not None:
+            info[self.fail_problem] = 3
         return nlml, None
 
     def gpr_batched_adam(self, X, Y, u, m, v, noises, lr_t, b1, b2, eps, fix_rho=False, loss_hist=None, theta_out=None, info=None):
         self.calls.append(("adam", u.shape, len(lr_t), fix_rho))
         u -= 0.01 * len(lr_t)  # "training": every unconstrained variable moves the same way
         loss_hist[:] = np.arange(len(lr_t))[:, None] + np.arange(u.shape[0])[None, :]
+        if self.fail_problem is not None:
+            info[self.fail_problem] = 3
+            loss_hist[:, self.fail_problem] = np.nan
         return loss_hist, theta_out
 
     def gpr_predict(self, X, y, Xnew, theta, noise):
@@ -274,6 +313,14 @@ def test_multibin_host_logic_with_fake_handle():
     mean, var = mdl.predict_f(X[:5])
     assert mean.shape == (5, 4) and var.shape == (5, 4)
     np.testing.assert_allclose(mean[0], mdl.best_thetas()[:, 0])  # each bin predicted with its own best theta
+    # a restart whose Cholesky fails is recorded, not raised: counters advance, selection skips it
+    fh.fail_problem = int(best[1]) * 4 + 1  # the restart that is currently best for bin 1
+    mdl.optimize(max_iters=3, learning_rate=0.1)
+    assert mdl.iterations == 15 and mdl.loss_history.shape == (15, 3, 4)
+    assert mdl.failed[best[1], 1] == 3 and np.count_nonzero(mdl.failed) == 1
+    assert np.isnan(mdl.training_loss()[best[1], 1])
+    assert mdl.best_restart()[1] != best[1]
+    fh.fail_problem = None
     frozen = MultiBinMFGP(X, Y, num_restarts=1, use_rho=False, handle=fh)
     frozen.optimize(max_iters=2)
     assert fh.calls[-1] == ("adam", (4, 9), 2, True)

@@ -90,3 +90,36 @@ def test_device_loop_equals_host_driven_loop_bitwise():
         opt.step([u], [g[:, :-1] * dsoftplus(th)])
     np.testing.assert_allclose(model.loss_history.reshape(15, B), np.array(hist), rtol=1e-12)
     np.testing.assert_allclose(model.u, u, rtol=1e-10, atol=1e-12)
+
+
+def test_failed_restart_is_per_problem_status_not_an_abort():
+    """with a per-problem info[] a non-positive pivot is that problem's status; the others train on."""
+    from multi_fidelity_gpflow_b200 import _lib
+    from multi_fidelity_gpflow_b200.optimizers import adam_step_factors
+
+    h = _lib.default_handle()
+    ds = onp.load_dataset("hbs")
+    X, Y = ds["X"], np.ascontiguousarray(ds["Y"][:, :4])
+    B, steps = 4, 6
+    u0 = onp.softplus_inv(np.ones((B, 13)))
+    lr_t, b1, b2 = adam_step_factors(0.05, steps)
+    good = np.full(B, 1e-3)
+    bad = good.copy()
+    bad[2] = -5.0  # K - 5 I: not positive definite from the first pivot on
+    ref_u, ref_hist = u0.copy(), np.empty((steps, B))
+    h.gpr_batched_adam(X, Y, ref_u, np.zeros_like(u0), np.zeros_like(u0), good, lr_t, b1, b2, loss_hist=ref_hist)
+    u, hist, info = u0.copy(), np.empty((steps, B)), np.zeros(B, dtype=np.int32)
+    h.gpr_batched_adam(X, Y, u, np.zeros_like(u0), np.zeros_like(u0), bad, lr_t, b1, b2, loss_hist=hist, info=info)  # no raise
+    assert info[2] > 0 and np.all(info[[0, 1, 3]] == 0)
+    keep = [0, 1, 3]
+    np.testing.assert_array_equal(u[keep], ref_u[keep])
+    np.testing.assert_array_equal(hist[:, keep], ref_hist[:, keep])
+    assert not np.isfinite(hist[:, 2]).any()
+    with pytest.raises(_lib.NotPositiveDefiniteError):  # without info[] the status is the call's error, as before
+        h.gpr_batched_adam(X, Y, u0.copy(), np.zeros_like(u0), np.zeros_like(u0), bad, lr_t, b1, b2)
+    # single evaluation: same convention
+    info2 = np.zeros(B, dtype=np.int32)
+    nl, _ = h.gpr_batched_nlml_grad(X, Y, np.ones((B, 13)), bad, info=info2)
+    assert info2[2] > 0 and np.isfinite(nl[keep]).all()
+    with pytest.raises(_lib.NotPositiveDefiniteError):
+        h.gpr_batched_nlml_grad(X, Y, np.ones((B, 13)), bad)

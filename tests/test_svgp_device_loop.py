@@ -72,3 +72,56 @@ def test_frozen_parameters_stay_put():
     mdl.optimize_on_device((X, Y), max_iters=5, initial_lr=0.01)
     assert np.array_equal(mdl.kernel.W.numpy(), W0) and np.array_equal(mdl.likelihood.variance.numpy(), lv0)
     assert mdl.loss_history[-1] < mdl.loss_history[0]
+
+
+@pytest.mark.parametrize("kind", ["hetero", "masked"])
+def test_likelihood_variants_device_loop_equals_host_loop(kind):
+    """HeteroscedasticGaussian's variance transform has lower bound 0 (linear_svgp.py:240), not the 1e-6 of
+    gpflow's Gaussian; MaskedGaussian trains one variance per output.  Both loops must follow the same trajectory."""
+    from multi_fidelity_gpflow_b200.linear_svgp import LatentMFCoregionalizationSVGP
+
+    ds = onp.load_dataset("hbs")
+    rng = np.random.default_rng(5)
+    X, Y = ds["X"], ds["Y"].copy()
+    kL, kD = _kernels(5)
+    if kind == "hetero":
+        Yt = np.hstack([Y, 0.05 + 0.1 * rng.random(Y.shape)])
+        a = LatentMFCoregionalizationSVGP(X, Yt, kL, kD, num_latents=4, num_inducing=20, heterosed=True)
+        a.likelihood.variance.assign(np.array([2e-6]))  # close to 0: a 1e-6 lower bound would change theta by 50 %
+        assert a.likelihood.variance.transform.lower == 0.0
+    else:
+        Y[rng.random(Y.shape) < 0.25] = np.nan
+        Yt = Y
+        a = LatentMFCoregionalizationSVGP(X, Yt, kL, kD, num_latents=4, num_inducing=20, num_outputs=49, masked=True)
+        assert a.likelihood.variance.shape == (49,)
+    b = copy.deepcopy(a)
+    a.optimize((X, Yt), max_iters=8, initial_lr=0.01, verbose=False)
+    b.optimize_on_device((X, Yt), max_iters=8, initial_lr=0.01)
+    np.testing.assert_allclose(b.loss_history, a.loss_history, rtol=1e-10)
+    for pa, pb in zip(_params(a), _params(b)):
+        np.testing.assert_allclose(pb, pa, rtol=1e-8, atol=1e-10)
+
+
+def test_device_loop_history_semantics_follow_the_reference_loops():
+    """linear_svgp.py:194 runs range(len(loss_history), max_iters) with a fresh optimizer; singlebin_svgp.py:79 resets."""
+    from multi_fidelity_gpflow_b200.linear_svgp import LatentMFCoregionalizationSVGP
+    from multi_fidelity_gpflow_b200.singlebin_svgp import SingleBinSVGP
+
+    ds = onp.load_dataset("hbs")
+    X, Y = ds["X"], ds["Y"]
+    kL, kD = _kernels(5)
+    a = LatentMFCoregionalizationSVGP(X, Y, kL, kD, num_latents=3, num_inducing=16, num_outputs=49)
+    b = copy.deepcopy(a)
+    a.optimize((X, Y), max_iters=4, initial_lr=0.01, verbose=False)
+    a.optimize((X, Y), max_iters=9, initial_lr=0.01, verbose=False)  # 5 more steps, optimizer restarted
+    b.optimize_on_device((X, Y), max_iters=4, initial_lr=0.01)
+    b.optimize_on_device((X, Y), max_iters=9, initial_lr=0.01)
+    assert len(b.loss_history) == len(a.loss_history) == 9 and len(b.kl_history) == 9
+    np.testing.assert_allclose(b.loss_history, a.loss_history, rtol=1e-10)
+    b.optimize_on_device((X, Y), max_iters=9, initial_lr=0.01)  # nothing left to do
+    assert len(b.loss_history) == 9
+    Y6 = np.ascontiguousarray(Y[:, :6])
+    s = SingleBinSVGP(X, Y6, kL, kD, 6, ds["Z_kmeans50"])
+    s.optimize_on_device((X, Y6), max_iters=3, initial_lr=0.01)
+    s.optimize_on_device((X, Y6), max_iters=5, initial_lr=0.01)
+    assert len(s.loss_history) == 5  # reset, like the reference
