@@ -63,3 +63,24 @@ class PowerSpecs:
     def test_arrays(self, fidelity: float = 1.0):
         xt = self.X_test_norm[0]
         return np.hstack([xt, np.full((xt.shape[0], 1), fidelity)]), self.Y_test[0]
+
+
+def synthetic_two_fidelity(N, d=10, seed=0):
+    """BASELINE config 5 / SURVEY 8(d) C5: synthetic two-fidelity exact-GPR problem of N points in d dimensions.  The first
+    7N/8 rows are low fidelity at uniform random inputs, the last N/8 high fidelity at a random subset of them (nested
+    designs, like the in-repo datasets); f_L = sum_k sin(2 pi x_k), f_H = 1.5 f_L + 0.3 cos(2 pi x_0), noise sd 0.03.
+    Returns (X [N, d+1], Y [N, 1], theta [2d+3], noise) with the configuration's hyper-parameters: lengthscales
+    linspace(0.5, 1, d) for both kernels, unit variances, rho = 1, noise variance 1e-3."""
+    rng = np.random.default_rng(seed)
+    n_hi = N // 8
+    n_lo = N - n_hi
+    x_lo = rng.random((n_lo, d))
+    x_hi = x_lo[rng.permutation(n_lo)[:n_hi]]
+    wave = lambda x: np.sin(2.0 * np.pi * x).sum(axis=1)
+    y_lo = wave(x_lo) + 0.03 * rng.standard_normal(n_lo)
+    y_hi = 1.5 * wave(x_hi) + 0.3 * np.cos(2.0 * np.pi * x_hi[:, 0]) + 0.03 * rng.standard_normal(n_hi)
+    X = np.zeros((N, d + 1))
+    X[:n_lo, :d], X[n_lo:, :d], X[n_lo:, d] = x_lo, x_hi, 1.0
+    ls = np.linspace(0.5, 1.0, d)
+    theta = np.concatenate([[1.0], ls, [1.0], ls, [1.0]])
+    return X, np.concatenate([y_lo, y_hi])[:, None], theta, 1e-3

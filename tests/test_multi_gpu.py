@@ -37,13 +37,33 @@ q_mu, q_sqrt = 0.1 * rng.standard_normal((M, L)), np.tile(0.3 * np.eye(M), (L, 1
 Z = ds["Z_kmeans50"]
 fn = lambda Xr, Yr, scale, klm: h.svgp_elbo_grad(Xr, Yr, Z, ths, W, q_mu, q_sqrt, 0.8, scale=scale, kl_mult=klm)
 out = dp_svgp_value_and_grad(fn, X, Y, num_data=53, kl_mult=1.3)
+# data-parallel TRAINING loop on device memory: two ranks against one rank (sub-group of rank 0) and the plain device loop
+import copy
+from multi_fidelity_gpflow_b200.kernels import SquaredExponential
+from multi_fidelity_gpflow_b200.linear_svgp import LatentMFCoregionalizationSVGP
+solo = dist.new_group([0])
+mk = lambda: LatentMFCoregionalizationSVGP(X, Y, SquaredExponential(lengthscales=np.ones(5)), SquaredExponential(lengthscales=np.ones(5)),
+                                           num_latents=4, num_inducing=20, num_outputs=49, handle=h)
+m2 = mk()
+m2.optimize_data_parallel((X, Y), max_iters=6, initial_lr=0.01, kl_multiplier=1.3)
+checksum = torch.tensor([float(np.sum(m2.q_mu.numpy())), float(m2.loss_history[-1])], dtype=torch.float64, device="cuda")
+both = [torch.empty_like(checksum) for _ in range(world)]
+dist.all_gather(both, checksum)
+if rank == 0:
+    m1, m0 = mk(), mk()
+    m1.optimize_data_parallel((X, Y), max_iters=6, initial_lr=0.01, kl_multiplier=1.3, group=solo)
+    m0.optimize_on_device((X, Y), max_iters=6, initial_lr=0.01, kl_multiplier=1.3)
+    dp = {"ranks_identical": bool(torch.equal(both[0], both[1])),
+          "loss_2v1": float(np.max(np.abs(np.array(m2.loss_history) / np.array(m1.loss_history) - 1))),
+          "loss_1v0": float(np.max(np.abs(np.array(m1.loss_history) / np.array(m0.loss_history) - 1))),
+          "qmu_2v1": float(np.max(np.abs(m2.q_mu.numpy() - m1.q_mu.numpy())) / np.max(np.abs(m1.q_mu.numpy())))}
 if rank == 0:
     ref_n, ref_g = h.gpr_batched_nlml_grad(X, Y, th, nz)
     ref = h.svgp_elbo_grad(X, Y, Z, ths, W, q_mu, q_sqrt, 0.8, scale=1.0, kl_mult=1.3)
     ok = bool(np.array_equal(full_n, ref_n) and np.array_equal(full_g, ref_g))
     err = {k: float(np.max(np.abs(np.asarray(out[k]) - np.asarray(ref[k]))) / (np.max(np.abs(np.asarray(ref[k]))) + 1e-300))
            for k in ("g_Z", "g_thetas", "g_q_mu", "g_q_sqrt", "g_W", "g_lik_var", "elbo")}
-    print("RESULT " + json.dumps({"bins_bit_identical": ok, "err": err}))
+    print("RESULT " + json.dumps({"bins_bit_identical": ok, "err": err, "dp": dp}))
 dist.destroy_process_group()
 ''' % ROOT
 
@@ -64,6 +84,35 @@ def test_two_gpu_sharding_and_dp_svgp(tmp_path):
     r = json.loads(line[7:])
     assert r["bins_bit_identical"]
     assert all(v < 1e-10 for v in r["err"].values()), r
+    dp = r["dp"]
+    assert dp["ranks_identical"] and dp["loss_2v1"] < 1e-10 and dp["loss_1v0"] < 1e-12 and dp["qmu_2v1"] < 1e-8, dp
+
+
+def test_two_handles_in_one_process():
+    """ADVICE r1 / include/mfgp.h threading contract: one handle per GPU in ONE process.  Function attributes (the > 48 KB
+    dynamic shared-memory opt-in of the GEMM, potrf, covariance and K6 kernels) are per device, so the second device must
+    get its own opt-in: run every large-smem kernel family on device 1 after device 0 has used them."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from multi_fidelity_gpflow_b200 import _lib
+    from oracle import mfgp_oracle as onp
+
+    ds = onp.load_dataset("hbs")
+    X, Y = ds["X"], ds["Y"]
+    big = onp.synthetic_exact_dataset(1500)
+    th = np.tile(onp.default_theta(5), (49, 1))
+    res = []
+    for dev in (0, 1):
+        h = _lib.Handle(dev)
+        nl, gr = h.gpr_batched_nlml_grad(X, Y, th, np.full(49, 1e-3))                         # K6
+        v, g = h.gpr_nlml_grad(big["X"], big["Y"], big["theta"], big["noise"])               # cov stream, potrf, trtri, gemm, cov_grad
+        K = h.cov(big["X"][:200], big["X"][200:500], big["theta"])                           # cov tile kernel
+        res.append((nl, gr, v, g, K))
+        h.close()
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)  # same kernels, same launch shapes on both devices: bit-identical
 
 
 CHOL_WORKER = r"""

@@ -125,3 +125,40 @@ def test_device_loop_history_semantics_follow_the_reference_loops():
     s.optimize_on_device((X, Y6), max_iters=3, initial_lr=0.01)
     s.optimize_on_device((X, Y6), max_iters=5, initial_lr=0.01)
     assert len(s.loss_history) == 5  # reset, like the reference
+
+
+def test_data_parallel_loop_on_one_rank_equals_device_loop():
+    """dist.dp_svgp_adam (mfgp_svgp_constrain / _elbo_grad_flat / _adam_update + an in-place NCCL all-reduce) with a
+    one-rank NCCL group: the same trajectory as mfgp_svgp_adam.  Runs on the single-GPU test box; the two-rank version
+    is tests/test_multi_gpu.py and the bench's --gpus N leg."""
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    from multi_fidelity_gpflow_b200.linear_svgp import LatentMFCoregionalizationSVGP
+
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", str(29700 + os.getpid() % 200))
+        torch.cuda.set_device(0)
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+        created = True
+    try:
+        ds = onp.load_dataset("hbs")
+        X, Y = ds["X"], ds["Y"]
+        kL, kD = _kernels(5)
+        a = LatentMFCoregionalizationSVGP(X, Y, kL, kD, num_latents=4, num_inducing=20, num_outputs=49)
+        b = copy.deepcopy(a)
+        a.optimize_on_device((X, Y), max_iters=7, initial_lr=0.01, kl_multiplier=1.5)
+        t = {}
+        b.optimize_data_parallel((X, Y), max_iters=7, initial_lr=0.01, kl_multiplier=1.5, timing=t)
+        assert t["ms_per_step"] > 0
+        np.testing.assert_allclose(b.loss_history, a.loss_history, rtol=1e-12)
+        np.testing.assert_allclose(b.kl_history, a.kl_history, rtol=1e-12, atol=1e-14)
+        for pa, pb in zip(_params(a), _params(b)):
+            np.testing.assert_allclose(pb, pa, rtol=1e-12, atol=1e-14)
+    finally:
+        if created:
+            dist.destroy_process_group()
