@@ -185,7 +185,8 @@ int mfgp_gemm(mfgp_handle* h, char transa, char transb, int m, int n, int k, dou
 int mfgp_potrf(mfgp_handle* h, double* A, int N, long lda);
 /* Winv [N, N] = inv(L) for the lower factor produced by mfgp_potrf. */
 int mfgp_potrf_inv(mfgp_handle* h, double* A, int N, long lda, double* Winv, long ldw);
-/* FP64 pipe microbenchmarks (bench.py: measured FP64 peak).  kind 0: DFMA, 1: DMMA m8n8k4.
+/* FP64 pipe microbenchmarks (bench.py: measured FP64 peak).  kind 0: DFMA, 1: DMMA m8n8k4, 2: both interleaved with equal
+ * pipe time (tells whether the two share one datapath: same FLOP/s as either alone, or not: up to twice).
  * Returns achieved FLOP/s in *flops. */
 int mfgp_fp64_peak(mfgp_handle* h, int kind, int iters, double* flops);
 

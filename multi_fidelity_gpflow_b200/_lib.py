@@ -88,8 +88,62 @@ class SvgpCfg(C.Structure):
     ]
 
 
+# ---- DLPack consumer (dlpack.h, DLManagedTensor ABI v0) -------------------------------------------------------
+# TF tensors (tf.experimental.dlpack.to_dlpack), CuPy / JAX arrays and anything else with __dlpack__ cross the C-ABI
+# zero-copy: the capsule's DLManagedTensor is read with ctypes, checked (float64, C-contiguous, CPU / CUDA memory) and its
+# data address passed to the library, which decides host vs device by itself (cudaPointerGetAttributes).
+class _DLDevice(C.Structure):
+    _fields_ = [("device_type", C.c_int), ("device_id", C.c_int)]
+
+
+class _DLDataType(C.Structure):
+    _fields_ = [("code", C.c_uint8), ("bits", C.c_uint8), ("lanes", C.c_uint16)]
+
+
+class _DLTensor(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("device", _DLDevice), ("ndim", C.c_int), ("dtype", _DLDataType),
+                ("shape", C.POINTER(C.c_int64)), ("strides", C.POINTER(C.c_int64)), ("byte_offset", C.c_uint64)]
+
+
+class _DLManagedTensor(C.Structure):
+    _fields_ = [("dl_tensor", _DLTensor), ("manager_ctx", C.c_void_p), ("deleter", C.c_void_p)]
+
+
+_KDL_FLOAT = 2
+_DL_DEVICES = {1: "cpu", 2: "cuda", 3: "cuda_host", 13: "cuda_managed"}
+_capsule_get = C.pythonapi.PyCapsule_GetPointer
+_capsule_get.restype, _capsule_get.argtypes = C.c_void_p, [C.py_object, C.c_char_p]
+_capsule_valid = C.pythonapi.PyCapsule_IsValid
+_capsule_valid.restype, _capsule_valid.argtypes = C.c_int, [C.py_object, C.c_char_p]
+
+
+def _is_capsule(x):
+    return type(x).__name__ == "PyCapsule"
+
+
+def from_dlpack_capsule(capsule, dtype_code=_KDL_FLOAT, bits=64):
+    """(address, shape, device kind) of an UNCONSUMED "dltensor" capsule.  The capsule stays owned by the caller (it is
+    not renamed to "used_dltensor"): its deleter runs when the capsule is garbage-collected, after the library call."""
+    if not _capsule_valid(capsule, b"dltensor"):
+        raise TypeError("expected an unconsumed DLPack capsule named 'dltensor'")
+    t = C.cast(_capsule_get(capsule, b"dltensor"), C.POINTER(_DLManagedTensor)).contents.dl_tensor
+    if (t.dtype.code, t.dtype.bits, t.dtype.lanes) != (dtype_code, bits, 1):
+        raise TypeError(f"DLPack tensor must be float{bits} (got code {t.dtype.code}, {t.dtype.bits} bits, {t.dtype.lanes} lanes)")
+    if t.device.device_type not in _DL_DEVICES:
+        raise TypeError(f"DLPack device type {t.device.device_type} is neither CPU nor CUDA memory")
+    shape = tuple(int(t.shape[i]) for i in range(t.ndim))
+    if bool(t.strides):  # NULL = compact row-major
+        expect = 1
+        for i in range(t.ndim - 1, -1, -1):
+            if shape[i] != 1 and int(t.strides[i]) != expect:
+                raise ValueError("DLPack tensor must be C-contiguous")
+            expect *= shape[i]
+    return (t.data or 0) + int(t.byte_offset), shape, _DL_DEVICES[t.device.device_type]
+
+
 def _ptr(x):
-    """Raw address of a float64/int32 C-contiguous buffer (host ndarray or device tensor)."""
+    """Raw address of a float64/int32 C-contiguous buffer: host ndarray, torch / CuPy device tensor, a DLPack capsule, or
+    any object exporting __dlpack__ (TF eager tensors, JAX arrays)."""
     if x is None:
         return None
     if isinstance(x, np.ndarray):
@@ -102,12 +156,20 @@ def _ptr(x):
         return C.c_void_p(x.data_ptr())
     if hasattr(x, "__cuda_array_interface__"):
         return C.c_void_p(x.__cuda_array_interface__["data"][0])
+    if _is_capsule(x) or hasattr(x, "__dlpack__"):
+        cap = x if _is_capsule(x) else x.__dlpack__()
+        addr, _, _ = from_dlpack_capsule(cap)
+        p = C.c_void_p(addr)
+        p._dlpack_owner = cap  # keeps the exporter's memory alive for as long as the pointer object lives (the call)
+        return p
     raise TypeError(f"unsupported buffer type {type(x)}")
 
 
 def as_f64(x):
-    """Host arrays -> contiguous float64 ndarray; device tensors pass through (must be float64)."""
+    """Host arrays -> contiguous float64 ndarray; device tensors and DLPack exporters pass through (must be float64)."""
     if hasattr(x, "data_ptr") or hasattr(x, "__cuda_array_interface__"):
+        return x
+    if not isinstance(x, np.ndarray) and hasattr(x, "__dlpack__") and hasattr(x, "shape"):
         return x
     return np.ascontiguousarray(x, dtype=np.float64)
 
@@ -122,6 +184,12 @@ class Handle:
             raise MFGPError(f"mfgp_create(device={device}) failed with {rc}: no usable CUDA device (no CPU fallback)")
         self._h = h
         self.device = device
+
+    def __deepcopy__(self, memo):
+        return self  # a handle is a device resource (stream, workspaces): copies of a model share it
+
+    def __copy__(self):
+        return self
 
     def close(self):
         if getattr(self, "_h", None):
@@ -175,7 +243,7 @@ class Handle:
             N2 = N
         theta = as_f64(theta)
         K = np.empty((N, N2)) if out is None else out
-        self._check(_lib.mfgp_cov(self._h, _ptr(X), N, _ptr(X2), N2, d, _ptr(theta), _ptr(K), K.shape[1] if K.ndim == 2 else N2), "mfgp_cov")
+        self._check(_lib.mfgp_cov(self._h, _ptr(X), N, _ptr(X2), N2, d, _ptr(theta), _ptr(K), K.shape[1] if len(K.shape) == 2 else N2), "mfgp_cov")
         return K
 
     def cov_diag(self, X, theta, out=None):

@@ -541,6 +541,37 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) 
     if (s == 123.456) out[0] = s;
 }
 
+// kind 2: both instruction streams in one loop, sized for equal pipe time (8 DMMA x 16 cycles = 64 DFMA x 2 cycles per
+// sub-partition): if DMMA and DFMA share one FP64 datapath the loop takes the SUM of the two times (same FLOP/s as either
+// alone), if they are separate units it takes the MAX (twice the FLOP/s).  The answer decides what "FP64 pipe busy" can
+// mean for a kernel that mixes both, like K6.
+__global__ void __launch_bounds__(256) dmix_peak_kernel(double* out, int iters) {
+    double c[8][2], a[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+    const double am = 1.0 + 1e-9 * threadIdx.x, bm = 1e-9, x = 1.0000001, y = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                             : "+d"(c[2 * r + i][0]), "+d"(c[2 * r + i][1])
+                             : "d"(am), "d"(bm));
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = fma(a[i], x, y);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 123.456) out[0] = s;
+}
+
 int mfgp_fp64_peak(mfgp_handle* h, int kind, int iters, double* flops) {
     CHECK_H(h);
     if (!flops || iters < 1) return MFGP_ERR_ARG;
@@ -555,14 +586,16 @@ int mfgp_fp64_peak(mfgp_handle* h, int kind, int iters, double* flops) {
     for (int rep = 0; rep < 4; ++rep) {
         cudaEventRecord(e0, h->stream);
         if (kind == 0) dfma_peak_kernel<<<blocks, 256, 0, h->stream>>>(d, iters);
-        else dmma_peak_kernel<<<blocks, 256, 0, h->stream>>>(d, iters);
+        else if (kind == 1) dmma_peak_kernel<<<blocks, 256, 0, h->stream>>>(d, iters);
+        else dmix_peak_kernel<<<blocks, 256, 0, h->stream>>>(d, iters);
         cudaEventRecord(e1, h->stream);
         cudaEventSynchronize(e1);
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
         if (rep > 0 && ms < best) best = ms;
     }
-    const double per_thread = kind == 0 ? 16.0 * 2.0 : 16.0 * (2.0 * 8 * 8 * 4) / 32.0;
+    const double per_thread = kind == 0 ? 16.0 * 2.0 : kind == 1 ? 16.0 * (2.0 * 8 * 8 * 4) / 32.0
+                                                     : 8.0 * (2.0 * 8 * 8 * 4) / 32.0 + 64.0 * 2.0;
     *flops = per_thread * iters * 256.0 * blocks / (best * 1e-3);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

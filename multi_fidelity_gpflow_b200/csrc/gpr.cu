@@ -66,16 +66,26 @@ __global__ void predict_var_kernel(const double* __restrict__ As, int N, int Ns,
     var[j] = kss[j] - s;
 }
 
-struct Factor {
-    double *K, *W, *G, *dinv, *logd, *Yw, *a;
-    long ld, strideM;
-    int Pp;
-};
+using Factor = GprFactor;
 
 // Assemble + factor + invert + a = W Y for `batch` problems.  theta_d/noise_d are device arrays.
 int factor(mfgp_handle* h, Scope& sc, const double* X, const double* Y, long ldy, int per_batch_cols, int b_off,
-           int ycols, int N, int d, int P, int batch, const double* theta_d, const double* noise_d, int* info_vec, bool need_G, Factor& f) {
-    cudaStream_t s = h->stream;
+           int ycols, int N, int d, int P, int batch, const double* theta_d, const double* noise_d, int* info_vec, Factor& f) {
+    MFGP_TRY(gpr_factor_alloc(h, sc, N, P, batch, f));
+    CovArgs c{};
+    c.Xa = X; c.Na = N; c.Xb = X; c.Nb = N; c.d = d;
+    c.theta = theta_d; c.theta_stride = 2 * d + 3;
+    c.K = f.K; c.ldk = f.ld; c.strideK = f.strideM;
+    c.symmetric = 1; c.mirror = 0;
+    c.diag_add = 0.0; c.diag_add_vec = noise_d;
+    c.batch = batch;
+    if (launch_cov(h->stream, c)) return mfgp_fail(h, MFGP_ERR_CUDA, "cov launch failed");
+    return gpr_factor_from_K(h, Y, ldy, per_batch_cols, b_off, ycols, N, P, batch, info_vec, f);
+}
+
+}  // namespace
+
+int gpr_factor_alloc(mfgp_handle* h, Scope& sc, int N, int P, int batch, GprFactor& f) {
     f.ld = round_up(N, 2);
     f.strideM = (long)N * f.ld;
     f.Pp = (int)round_up(P, 2);
@@ -86,18 +96,14 @@ int factor(mfgp_handle* h, Scope& sc, const double* X, const double* Y, long ldy
     f.logd = sc.alloc<double>((size_t)batch * N);
     f.Yw = sc.alloc<double>((size_t)batch * N * f.Pp);
     f.a = sc.alloc<double>((size_t)batch * N * f.Pp);
-    if (!sc.ok) return MFGP_ERR_CUDA;
-    (void)need_G;
+    (void)h;
+    return sc.ok ? 0 : MFGP_ERR_CUDA;
+}
 
-    CovArgs c{};
-    c.Xa = X; c.Na = N; c.Xb = X; c.Nb = N; c.d = d;
-    c.theta = theta_d; c.theta_stride = 2 * d + 3;
-    c.K = f.K; c.ldk = f.ld; c.strideK = f.strideM;
-    c.symmetric = 1; c.mirror = 0;
-    c.diag_add = 0.0; c.diag_add_vec = noise_d;
-    c.batch = batch;
-    if (launch_cov(s, c)) return mfgp_fail(h, MFGP_ERR_CUDA, "cov launch failed");
-
+// f.K holds the (lower triangle of the) noisy covariance: potrf -> W = L^-1 -> a = W Y.
+int gpr_factor_from_K(mfgp_handle* h, const double* Y, long ldy, int per_batch_cols, int b_off, int ycols, int N, int P,
+                      int batch, int* info_vec, GprFactor& f) {
+    cudaStream_t s = h->stream;
     CholArgs ch{};
     ch.A = f.K; ch.N = N; ch.lda = f.ld; ch.strideA = f.strideM; ch.batch = batch;
     ch.dinv = f.dinv; ch.logd = f.logd; ch.d_info = h->d_info; ch.aux = h->aux_stream; ch.ev = h->ev; ch.info_vec = info_vec;
@@ -117,17 +123,13 @@ int factor(mfgp_handle* h, Scope& sc, const double* X, const double* Y, long ldy
     return 0;
 }
 
-}  // namespace
+void gpr_nlml_from_factor(mfgp_handle* h, const GprFactor& f, int N, int P, int batch, double* nlml_d) {
+    nlml_kernel<<<batch, 256, 0, h->stream>>>(f.a, N, f.Pp, P, f.logd, nlml_d);
+}
 
-int gpr_nlml_grad_device(mfgp_handle* h, Scope& sc, const double* X, const double* Y, long ldy, int per_batch_cols,
-                         int b_off, int ycols, int N, int d, int P, int batch, const double* theta_d, const double* noise_d,
-                         double* nlml_d, double* grad_d, int* info_vec) {
+// f.G (lower tiles) <- alpha alpha^T - P K^-1 with alpha = W^T a, K^-1 = W^T W
+int gpr_build_G(mfgp_handle* h, Scope& sc, int N, int P, int batch, GprFactor& f) {
     cudaStream_t s = h->stream;
-    Factor f;
-    MFGP_TRY(factor(h, sc, X, Y, ldy, per_batch_cols, b_off, ycols, N, d, P, batch, theta_d, noise_d, info_vec, grad_d != nullptr, f));
-    nlml_kernel<<<batch, 256, 0, s>>>(f.a, N, f.Pp, P, f.logd, nlml_d);
-    if (!grad_d) return 0;
-
     const long strideV = (long)N * f.Pp;
     double* alpha = sc.alloc<double>((size_t)batch * strideV);
     if (!sc.ok) return MFGP_ERR_CUDA;
@@ -162,6 +164,18 @@ int gpr_nlml_grad_device(mfgp_handle* h, Scope& sc, const double* X, const doubl
     k.krange = KR_LO_MAXIJ;
     k.lower_only = 1;
     if (launch_gemm(s, k)) return mfgp_fail(h, MFGP_ERR_CUDA, "gemm (W^T W) failed");
+    return 0;
+}
+
+int gpr_nlml_grad_device(mfgp_handle* h, Scope& sc, const double* X, const double* Y, long ldy, int per_batch_cols,
+                         int b_off, int ycols, int N, int d, int P, int batch, const double* theta_d, const double* noise_d,
+                         double* nlml_d, double* grad_d, int* info_vec) {
+    cudaStream_t s = h->stream;
+    Factor f;
+    MFGP_TRY(factor(h, sc, X, Y, ldy, per_batch_cols, b_off, ycols, N, d, P, batch, theta_d, noise_d, info_vec, f));
+    gpr_nlml_from_factor(h, f, N, P, batch, nlml_d);
+    if (!grad_d) return 0;
+    MFGP_TRY(gpr_build_G(h, sc, N, P, batch, f));
 
     CovGradArgs cg{};
     cg.Xa = X; cg.Na = N; cg.Xb = X; cg.Nb = N; cg.d = d;
@@ -184,7 +198,7 @@ int gpr_predict_device(mfgp_handle* h, Scope& sc, const double* X, const double*
                        double* var_d) {
     cudaStream_t s = h->stream;
     Factor f;
-    MFGP_TRY(factor(h, sc, X, Y, P, 0, 0, 0, N, d, P, 1, theta_d, noise_d, nullptr, false, f));
+    MFGP_TRY(factor(h, sc, X, Y, P, 0, 0, 0, N, d, P, 1, theta_d, noise_d, nullptr, f));
     const long lds = round_up(Ns, 2);
     double* Ks = sc.alloc<double>((size_t)N * lds);
     double* As = sc.alloc<double>((size_t)N * lds);

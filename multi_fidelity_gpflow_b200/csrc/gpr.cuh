@@ -10,3 +10,18 @@ int gpr_nlml_grad_device(mfgp_handle* h, Scope& sc, const double* X, const doubl
 int gpr_predict_device(mfgp_handle* h, Scope& sc, const double* X, const double* Y, int N, int d, int P,
                        const double* Xs, int Ns, const double* theta_d, const double* noise_d, double* mean_d,
                        double* var_d);
+
+// Pieces of the pipeline, shared with the graph-kernel model (graph.cu): workspaces of `batch` problems of size N ...
+struct GprFactor {
+    double *K, *W, *G, *dinv, *logd, *Yw, *a;
+    long ld, strideM;
+    int Pp;
+};
+int gpr_factor_alloc(mfgp_handle* h, Scope& sc, int N, int P, int batch, GprFactor& f);
+// ... K (lower triangle valid, noise included) -> L, W = L^-1, a = W Y ...
+int gpr_factor_from_K(mfgp_handle* h, const double* Y, long ldy, int per_batch_cols, int b_off, int ycols, int N, int P,
+                      int batch, int* info_vec, GprFactor& f);
+// ... nlml = 1/2 |a|^2 + P sum log L_ii + N P / 2 log 2 pi ...
+void gpr_nlml_from_factor(mfgp_handle* h, const GprFactor& f, int N, int P, int batch, double* nlml_d);
+// ... and f.G (lower tiles) <- alpha alpha^T - P K^-1.
+int gpr_build_G(mfgp_handle* h, Scope& sc, int N, int P, int batch, GprFactor& f);

@@ -269,9 +269,11 @@ def test_batched_not_pd_reports_per_problem_info(h):
     th = np.tile(onp.default_theta(2), (3, 1))
     nz = np.array([1e-3, -1e-3, 1e-3])
     info = np.zeros(3, dtype=np.int32)
-    with pytest.raises(NotPositiveDefiniteError):
-        h.gpr_batched_nlml_grad(X, Y, th, nz, info=info)
+    nl, _ = h.gpr_batched_nlml_grad(X, Y, th, nz, info=info)  # per-problem status: no exception
     assert info[0] == 0 and info[2] == 0 and info[1] > 0
+    assert np.isfinite(nl[[0, 2]]).all() and not np.isfinite(nl[1])
+    with pytest.raises(NotPositiveDefiniteError):  # without info[] the failure is the call's error
+        h.gpr_batched_nlml_grad(X, Y, th, nz)
 
 
 def test_cov_streaming_kernel_full_size_properties(h):
@@ -324,3 +326,27 @@ def test_cov_grad_contraction_vs_autograd(h, N, d):
     (torch.from_numpy(G) * K).sum().backward()
     ref = -0.5 * np.concatenate([tht.grad.numpy(), [np.trace(G)]])
     np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+
+
+def test_dlpack_device_exporter_zero_copy(h):
+    """A CUDA tensor that only speaks DLPack (as a TF / JAX tensor would) crosses the C-ABI as a device pointer."""
+    import torch
+
+    from multi_fidelity_gpflow_b200 import _lib
+
+    class OnlyDLPack:
+        def __init__(self, t):
+            self._t, self.shape = t, tuple(t.shape)
+
+        def __dlpack__(self, stream=None):
+            return self._t.__dlpack__()
+
+    rng = np.random.default_rng(0)
+    X, th = rand_X(rng, 300, 5), rand_theta(rng, 5)
+    Xd, thd = torch.from_numpy(X).cuda(), torch.from_numpy(th).cuda()
+    Kd = torch.zeros(300, 300, dtype=torch.float64, device="cuda")
+    addr, shape, kind = _lib.from_dlpack_capsule(Xd.__dlpack__())
+    assert addr == Xd.data_ptr() and shape == (300, 6) and kind == "cuda"
+    h.cov(OnlyDLPack(Xd), None, OnlyDLPack(thd), out=OnlyDLPack(Kd))
+    assert h.sync() == 0
+    np.testing.assert_array_equal(Kd.cpu().numpy(), h.cov(X, None, th))
