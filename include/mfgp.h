@@ -99,6 +99,23 @@ int mfgp_gpr_batched_adam(mfgp_handle* h, const double* X, int N, int d, const d
                           double* u, double* m, double* v, const double* noise, const double* lr_t, double beta1,
                           double beta2, double eps, int fix_rho, int nsteps, double* loss_hist, double* theta_out, int* info);
 
+/* ---- Graph-structured multi-fidelity kernel ---------------------------------------------------
+ * replaces GraphMultiFidelityKernel.K / K_diag (mfgpflow/graph.py:39-93, :96-115) and, for GraphMultiFidelityGPModel
+ * (graph.py:118-188), GPR.log_marginal_likelihood + tape.gradient.  num_lf low-fidelity sources (fidelity column value
+ * i in [0, num_lf)) and one high-fidelity level (value num_lf); rows with any other value have zero covariance.
+ * gtheta (constrained values), length mfgp_graph_nparams(num_lf, d) = m + m^2 + (m + 1)(d + 1):
+ *   [rho (m)] [rho_LF (m x m, row-major, diagonal unused)] [ls_Li (d), var_Li] for i < m, [ls_delta (d), var_delta].
+ * Only K(X, X) exists: the reference's rectangular call is not shape-consistent (graph.py:76-79, :91).  K is the FULL
+ * N x N matrix including the 1e-6 jitter of graph.py:91; like the reference it is not symmetric once the low-fidelity
+ * kernels differ (graph.py:63 uses the row's kernel).  The objective factors the lower triangle of K + noise I and
+ * contracts the symmetric sensitivity with the derivative of every entry -- TensorFlow's Cholesky / gradient semantics.
+ * grad [nparams + 1] (or NULL): d nlml / d [gtheta, noise]; the entries of the unused rho_LF diagonal are 0. */
+int mfgp_graph_nparams(int num_lf, int d);
+int mfgp_graph_cov(mfgp_handle* h, const double* X, int N, int d, int num_lf, const double* gtheta, double* K, long ldk);
+int mfgp_graph_cov_diag(mfgp_handle* h, const double* X, int N, int d, int num_lf, const double* gtheta, double* out);
+int mfgp_graph_gpr_nlml_grad(mfgp_handle* h, const double* X, const double* Y, int N, int d, int P, int num_lf,
+                             const double* gtheta, double noise, double* nlml, double* grad);
+
 /* ---- K7/K8: sparse variational GP (whitened, shared inducing points) -------------------
  * replaces gpflow SVGP.elbo / prior_kl / predict_f as called at singlebin_svgp.py:83,97 and
  * linear_svgp.py:177,184,188,199 with kernels SeparateIndependent (W == NULL, L == P,

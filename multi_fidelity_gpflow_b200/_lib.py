@@ -50,6 +50,10 @@ def _load():
         "mfgp_gpr_predict": ([vp, vp, vp, i, i, i, vp, i, vp, d, vp, vp], i),
         "mfgp_gpr_batched_nlml_grad": ([vp, vp, i, i, vp, l, i, i, vp, vp, vp, vp, vp], i),
         "mfgp_gpr_batched_adam": ([vp, vp, i, i, vp, l, i, i, vp, vp, vp, vp, vp, d, d, d, i, i, vp, vp, vp], i),
+        "mfgp_graph_nparams": ([i, i], i),
+        "mfgp_graph_cov": ([vp, vp, i, i, i, vp, vp, l], i),
+        "mfgp_graph_cov_diag": ([vp, vp, i, i, i, vp, vp], i),
+        "mfgp_graph_gpr_nlml_grad": ([vp, vp, vp, i, i, i, i, vp, d, vp, vp], i),
         "mfgp_svgp_elbo_grad": ([vp, vp, vp, vp, vp, vp, vp, vp, vp, d, vp, vp, vp, vp, vp, vp, vp, vp], i),
         "mfgp_svgp_elbo_grad_v": ([vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp], i),
         "mfgp_svgp_predict": ([vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp], i),
@@ -74,7 +78,8 @@ _lib = _load()
 EXPORTED_SYMBOLS = [
     "mfgp_version", "mfgp_create", "mfgp_destroy", "mfgp_set_stream", "mfgp_reset_stream", "mfgp_set_async", "mfgp_sync",
     "mfgp_last_error", "mfgp_sm_count", "mfgp_cov", "mfgp_cov_diag", "mfgp_cov_grad", "mfgp_gpr_nlml", "mfgp_gpr_nlml_grad",
-    "mfgp_gpr_predict", "mfgp_gpr_batched_nlml_grad", "mfgp_gpr_batched_adam", "mfgp_svgp_elbo_grad", "mfgp_svgp_elbo_grad_v", "mfgp_svgp_predict", "mfgp_svgp_adam",
+    "mfgp_gpr_predict", "mfgp_gpr_batched_nlml_grad", "mfgp_gpr_batched_adam",
+    "mfgp_graph_nparams", "mfgp_graph_cov", "mfgp_graph_cov_diag", "mfgp_graph_gpr_nlml_grad", "mfgp_svgp_elbo_grad", "mfgp_svgp_elbo_grad_v", "mfgp_svgp_predict", "mfgp_svgp_adam",
     "mfgp_svgp_flat_size", "mfgp_svgp_constrain", "mfgp_svgp_elbo_grad_flat", "mfgp_svgp_adam_update", "mfgp_gemm",
     "mfgp_potrf", "mfgp_potrf_inv", "mfgp_fp64_peak",
 ]
@@ -336,6 +341,32 @@ class Handle:
         if not (rc > 0 and info is not None):  # per-problem status in info[]: the other problems' steps stand
             self._check(rc, "mfgp_gpr_batched_adam")
         return loss_hist, theta_out
+
+    # -- graph-structured multi-fidelity kernel (reference mfgpflow/graph.py) -------------------------------
+    def graph_cov(self, X, num_lf, gtheta):
+        X, gtheta = as_f64(X), as_f64(gtheta)
+        N, d = X.shape[0], X.shape[1] - 1
+        K = np.empty((N, N))
+        self._check(_lib.mfgp_graph_cov(self._h, _ptr(X), N, d, int(num_lf), _ptr(gtheta), _ptr(K), N), "mfgp_graph_cov")
+        return K
+
+    def graph_cov_diag(self, X, num_lf, gtheta):
+        X, gtheta = as_f64(X), as_f64(gtheta)
+        N, d = X.shape[0], X.shape[1] - 1
+        out = np.empty(N)
+        self._check(_lib.mfgp_graph_cov_diag(self._h, _ptr(X), N, d, int(num_lf), _ptr(gtheta), _ptr(out)), "mfgp_graph_cov_diag")
+        return out
+
+    def graph_gpr_nlml_grad(self, X, Y, num_lf, gtheta, noise, want_grad=True):
+        X, Y, gtheta = as_f64(X), as_f64(Y), as_f64(gtheta)
+        N, d, P = X.shape[0], X.shape[1] - 1, Y.shape[1]
+        n = _lib.mfgp_graph_nparams(int(num_lf), d)
+        if gtheta.shape != (n,):
+            raise ValueError(f"gtheta must have {n} entries for num_LF={num_lf}, d={d}")
+        out, g = np.empty(1), (np.empty(n + 1) if want_grad else None)
+        self._check(_lib.mfgp_graph_gpr_nlml_grad(self._h, _ptr(X), _ptr(Y), N, d, P, int(num_lf), _ptr(gtheta), float(noise),
+                                                  _ptr(out), _ptr(g)), "mfgp_graph_gpr_nlml_grad")
+        return float(out[0]), g
 
     # -- SVGP ----------------------------------------------------------------------------------
     def svgp_elbo_grad(self, X, Y, Z, thetas, W, q_mu, q_sqrt, lik_var, scale=1.0, kl_mult=1.0, hetero=False,

@@ -6,7 +6,7 @@ import numpy as np
 
 
 class Transform:
-    """theta = lower + softplus(u) (gpflow.utilities.positive(lower)) or identity."""
+    """theta = lower + softplus(u) (gpflow.utilities.positive(lower)), sigmoid(u) (tfp.bijectors.Sigmoid) or identity."""
 
     def __init__(self, kind="identity", lower=0.0):
         self.kind, self.lower = kind, float(lower)
@@ -14,23 +14,34 @@ class Transform:
     def forward(self, u):
         if self.kind == "identity":
             return np.array(u, dtype=np.float64, copy=True)
+        if self.kind == "sigmoid":
+            return 1.0 / (1.0 + np.exp(-np.asarray(u, dtype=np.float64)))
         return self.lower + np.logaddexp(0.0, u)
 
     def inverse(self, theta):
         theta = np.asarray(theta, dtype=np.float64)
         if self.kind == "identity":
             return theta.copy()
+        if self.kind == "sigmoid":
+            return np.log(theta) - np.log1p(-theta)
         x = theta - self.lower
         return x + np.log(-np.expm1(-x))
 
     def dtheta_du(self, theta):
         if self.kind == "identity":
             return np.ones_like(np.asarray(theta, dtype=np.float64))
+        if self.kind == "sigmoid":
+            t = np.asarray(theta, dtype=np.float64)
+            return t * (1.0 - t)
         return 1.0 - np.exp(-(np.asarray(theta, dtype=np.float64) - self.lower))
 
 
 def positive(lower=0.0):
     return Transform("softplus", lower)
+
+
+def sigmoid():
+    return Transform("sigmoid")
 
 
 class Parameter:

@@ -129,6 +129,75 @@ def mf_K_diag(X, theta):
 
 
 # --------------------------------------------------------------------------------------
+# reference graph kernel, mfgpflow/graph.py:39-115 (several LF sources)
+# --------------------------------------------------------------------------------------
+def graph_unpack(gtheta, m, d):
+    """gtheta layout of include/mfgp.h: rho [m], rho_LF [m, m], (ls_Li [d], var_Li) per source, ls_delta [d], var_delta."""
+    g = np.asarray(gtheta, dtype=np.float64)
+    rho, rho_LF = g[:m], g[m:m + m * m].reshape(m, m)
+    o = m + m * m
+    ks = []
+    for _ in range(m + 1):
+        ks.append((g[o:o + d], g[o + d]))
+        o += d + 1
+    return rho, rho_LF, ks[:m], ks[m]
+
+
+def graph_pack(rho, rho_LF, kernels_L, kernel_delta):
+    parts = [np.ravel(rho), np.ravel(rho_LF)]
+    for ls, var in list(kernels_L) + [kernel_delta]:
+        parts += [np.ravel(ls), [var]]
+    return np.concatenate([np.asarray(p, dtype=np.float64) for p in parts])
+
+
+def graph_K(X, gtheta, m):
+    """GraphMultiFidelityKernel.K(X) for X2 = X (graph.py:39-93), block by block in the reference's order, rho = rho[:, 0]."""
+    X = np.asarray(X, dtype=np.float64)
+    N, d = X.shape[0], X.shape[1] - 1
+    rho, rho_LF, kL, kD = graph_unpack(gtheta, m, d)
+    masks_L = [np.where(X[:, -1] == i)[0] for i in range(m)]  # :45
+    mask_H = np.where(X[:, -1] == m)[0]                       # :46
+    K = np.zeros((N, N))                                      # :54
+    for i in range(m):                                        # :57-66  LF-LF, the ROW source's kernel
+        for j in range(m):
+            Xi, Xj = X[masks_L[i], :-1], X[masks_L[j], :-1]
+            rho_ij = rho_LF[i, j] if i != j else 1.0
+            K[np.ix_(masks_L[i], masks_L[j])] = rho_ij * se_K(Xi, Xj, *kL[i])
+    if mask_H.size > 0:                                       # :69, :82
+        XH = X[mask_H, :-1]
+        for i in range(m):                                    # :70-79  LF-HF and HF-LF
+            XL = X[masks_L[i], :-1]
+            K[np.ix_(masks_L[i], mask_H)] = se_K(XL, XH, *kL[i]) * rho[i]
+            K[np.ix_(mask_H, masks_L[i])] = se_K(XH, XL, *kL[i]) * rho[i]
+        KHH = sum(se_K(XH, XH, *kL[i]) * rho[i] ** 2 for i in range(m)) + se_K(XH, XH, *kD)  # :84-85
+        K[np.ix_(mask_H, mask_H)] = KHH
+    return K + np.eye(N) * 1e-6                               # :91
+
+
+def graph_K_diag(X, gtheta, m):
+    """GraphMultiFidelityKernel.K_diag (graph.py:96-115)."""
+    X = np.asarray(X, dtype=np.float64)
+    d = X.shape[1] - 1
+    rho, _, kL, kD = graph_unpack(gtheta, m, d)
+    out = np.zeros(X.shape[0])
+    for i in range(m):
+        out[X[:, -1] == i] = kL[i][1]
+    out[X[:, -1] == m] = sum(kL[i][1] * rho[i] ** 2 for i in range(m)) + kD[1]
+    return out
+
+
+def graph_gpr_lml(X, Y, gtheta, m, noise):
+    """GPR.log_marginal_likelihood with the graph kernel (model graph.py:118-141).  tf.linalg.cholesky reads the LOWER
+    triangle of K + noise I only (K need not be symmetric, graph.py:63); so does np.linalg.cholesky."""
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    N = X.shape[0]
+    L = np.linalg.cholesky(np.tril(graph_K(X, gtheta, m) + noise * np.eye(N)) + np.tril(graph_K(X, gtheta, m), -1).T)
+    A = sla.solve_triangular(L, Y, lower=True)
+    return float(np.sum(-0.5 * np.sum(A * A, axis=0) - 0.5 * N * LOG2PI - np.sum(np.log(np.diag(L)))))
+
+
+# --------------------------------------------------------------------------------------
 # GPflow GPR (models/gpr.py, logdensities.py::multivariate_normal)
 # --------------------------------------------------------------------------------------
 def gpr_lml(X, Y, theta, noise):

@@ -101,6 +101,50 @@ def gpr_batched_value_and_grad(X, Y, thetas, noises):
     return vals, grads
 
 
+def graph_K(X, gtheta, m):
+    """GraphMultiFidelityKernel.K(X) (graph.py:39-93) written with masks; same values as oracle.mfgp_oracle.graph_K."""
+    X = _t(X)
+    N, d = X.shape[0], X.shape[1] - 1
+    rho, rho_LF = gtheta[:m], gtheta[m:m + m * m].reshape(m, m)
+    o = m + m * m
+    f = X[:, -1]
+    live = torch.zeros(N, dtype=torch.bool)
+    for i in range(m + 1):
+        live = live | (f == i)
+    x = torch.where(live[:, None], X[:, :-1], torch.zeros_like(X[:, :-1]))
+    ind = [(f == i).to(DT) for i in range(m + 1)]
+    kern = []
+    for i in range(m + 1):
+        kern.append(se_K(x, x, gtheta[o:o + d], gtheta[o + d]))
+        o += d + 1
+    K = torch.zeros((N, N), dtype=DT)
+    H = ind[m]
+    for i in range(m):
+        for j in range(m):
+            coef = rho_LF[i, j] if i != j else torch.ones((), dtype=DT)
+            K = K + coef * (ind[i][:, None] * ind[j][None, :]) * kern[i]
+        K = K + rho[i] * (ind[i][:, None] * H[None, :] + H[:, None] * ind[i][None, :]) * kern[i]
+        K = K + rho[i] ** 2 * (H[:, None] * H[None, :]) * kern[i]
+    K = K + (H[:, None] * H[None, :]) * kern[m]
+    return K + 1e-6 * torch.eye(N, dtype=DT)
+
+
+def graph_gpr_lml_value_and_grad(X, Y, gtheta, m, noise):
+    """LML of GraphMultiFidelityGPModel and its gradient w.r.t. the CONSTRAINED [gtheta, noise] exactly as
+    tape.gradient produces it: the (possibly asymmetric) K goes into the Cholesky as is -- torch.linalg.cholesky, like
+    tf.linalg.cholesky, reads the lower triangle and its backward returns the symmetrised sensitivity."""
+    X, Y = _t(X), _t(Y)
+    N, P = Y.shape
+    th = torch.tensor(np.asarray(gtheta, dtype=np.float64), requires_grad=True)
+    nz = torch.tensor(float(noise), dtype=DT, requires_grad=True)
+    Kn = graph_K(X, th, m) + nz * torch.eye(N, dtype=DT)
+    L = torch.linalg.cholesky(Kn)
+    A = torch.linalg.solve_triangular(L, Y, upper=False)
+    val = -0.5 * (A * A).sum() - P * (0.5 * N * LOG2PI + torch.log(torch.diagonal(L)).sum())
+    gth, gnz = torch.autograd.grad(val, [th, nz])
+    return float(val.detach()), gth.numpy().copy(), float(gnz)
+
+
 def prior_kl(q_mu, q_sqrt):
     M, L = q_mu.shape
     Lq = torch.tril(q_sqrt)
