@@ -15,6 +15,11 @@
 #define CHECK_H(h) \
     if (!(h)) return MFGP_ERR_ARG
 
+int launch_gpr_small(cudaStream_t s, const SmallArgs& a) {
+    static const int which = [] { const char* e = getenv("MFGP_SMALL_KERNEL"); return e ? atoi(e) : 5; }();
+    return which == 4 ? launch_gpr_small_v4(s, a) : launch_gpr_small_v5(s, a);
+}
+
 extern "C" {
 
 int mfgp_version(void) { return 100; }
@@ -195,7 +200,7 @@ static int gpr_common(mfgp_handle* h, const double* X, const double* Y, int N, i
         SmallArgs a{};
         a.X = dX; a.N = N; a.d = d; a.Y = dY; a.ldy = P; a.ycols = P; a.B = P;
         a.theta = th; a.noise = nz; a.nlml = nl; a.grad = gg; a.info = nullptr; a.d_info = h->d_info;
-        if (launch_gpr_small_v4(h->stream, a)) return mfgp_fail(h, MFGP_ERR_CUDA, "gpr_small launch failed");
+        if (launch_gpr_small(h->stream, a)) return mfgp_fail(h, MFGP_ERR_CUDA, "gpr_small launch failed");
         small_shared_reduce_kernel<<<1, 64, 0, h->stream>>>(nl, gg, P, np + 1, dn, dg);
         return sc.finish();
     }
@@ -273,7 +278,7 @@ static int batched_small_pipelined(mfgp_handle* h, const double* X, int N, int d
         a.X = dX; a.N = N; a.d = d; a.Y = dY; a.ldy = ldy; a.ycols = ycols; a.B = (int)nb; a.prob0 = (int)(b0 % ycols);
         a.theta = dth + b0 * np; a.noise = dnz + b0; a.nlml = dn + b0; a.grad = dg ? dg + b0 * (np + 1) : nullptr;
         a.info = di ? di + b0 : nullptr; a.d_info = h->d_info;
-        if (launch_gpr_small_v4(s, a)) rc = mfgp_fail(h, MFGP_ERR_CUDA, "gpr_small launch failed");
+        if (launch_gpr_small(s, a)) rc = mfgp_fail(h, MFGP_ERR_CUDA, "gpr_small launch failed");
         cudaEventRecord(ev[nch + c], s);
         cudaStreamWaitEvent(sout, ev[nch + c], 0);
         cudaMemcpyAsync(nlml + b0, dn + b0, (size_t)nb * 8, cudaMemcpyDeviceToHost, sout);
@@ -315,7 +320,7 @@ int mfgp_gpr_batched_nlml_grad(mfgp_handle* h, const double* X, int N, int d, co
         SmallArgs a{};
         a.X = dX; a.N = N; a.d = d; a.Y = dY; a.ldy = ldy; a.ycols = ycols; a.B = B;
         a.theta = dth; a.noise = dnz; a.nlml = dn; a.grad = dg; a.info = di; a.d_info = h->d_info;
-        if (launch_gpr_small_v4(h->stream, a))
+        if (launch_gpr_small(h->stream, a))
             return mfgp_fail(h, MFGP_ERR_CUDA, "gpr_small launch failed");
     } else {
         // blocked path, chunked so that 3 N^2 workspaces per problem fit comfortably
@@ -438,7 +443,7 @@ int mfgp_gpr_batched_adam(mfgp_handle* h, const double* X, int N, int d, const d
     a.X = dX; a.N = N; a.d = d; a.Y = dY; a.ldy = ldy; a.ycols = ycols; a.B = B;
     a.theta = dth; a.noise = dnz; a.nlml = dn; a.grad = dg; a.info = dsi; a.d_info = h->d_info;
     for (int s = 0; s < nsteps; ++s) {
-        if (launch_gpr_small_v4(h->stream, a)) return mfgp_fail(h, MFGP_ERR_CUDA, "gpr_small launch failed");
+        if (launch_gpr_small(h->stream, a)) return mfgp_fail(h, MFGP_ERR_CUDA, "gpr_small launch failed");
         adam_update_kernel<<<gb, tb, 0, h->stream>>>(du, dm, dv, dth, dg, dn, dlr, s, beta1, beta2, eps, fix_rho, np, B, dl, dsi, di);
     }
     if (dto) CUDA_TRY(h, cudaMemcpyAsync(dto, dth, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));

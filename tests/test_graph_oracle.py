@@ -8,11 +8,11 @@ from oracle import mfgp_oracle as onp
 from oracle import mfgp_oracle_torch as otc
 
 
-def graph_problem(rng, N=40, d=3, m=2, P=2, symmetric=False):
+def graph_problem(rng, N=40, d=3, m=2, P=2, symmetric=False, noise=1e-3, max_draws=200):
     """Random graph-model problem.  The reference's construction is not positive semi-definite in general (K_HH has no
-    rho_i rho_j rho_LF_ij cross terms, graph.py:84): draw short length-scales / weak cross-correlations and redraw until the
-    lower-triangle matrix the Cholesky sees is safely positive definite."""
-    while True:
+    rho_i rho_j rho_LF_ij cross terms, graph.py:84): draw short length-scales / weak cross-correlations and redraw (a bounded
+    number of times) until the matrix the Cholesky sees -- lower triangle of K + noise I -- is positive definite with margin."""
+    for _ in range(max_draws):
         X = np.hstack([rng.random((N, d)), rng.integers(0, m + 1, size=(N, 1)).astype(float)])
         Y = rng.standard_normal((N, P))
         rho = 0.5 + rng.random(m)
@@ -24,8 +24,9 @@ def graph_problem(rng, N=40, d=3, m=2, P=2, symmetric=False):
         kD = (0.3 + 0.2 * rng.random(d), 0.5 + rng.random())
         gth = onp.graph_pack(rho, rho_LF, kL, kD)
         K = onp.graph_K(X, gth, m)
-        if np.linalg.eigvalsh(np.tril(K) + np.tril(K, -1).T).min() > 1e-2:
+        if np.linalg.eigvalsh(np.tril(K) + np.tril(K, -1).T).min() + noise > 0.3 * noise:
             return X, Y, gth
+    raise RuntimeError(f"no positive-definite graph-kernel problem in {max_draws} draws (N={N}, d={d}, m={m})")
 
 
 def test_numpy_and_torch_forms_agree_and_structure():
