@@ -15,11 +15,6 @@
 #define CHECK_H(h) \
     if (!(h)) return MFGP_ERR_ARG
 
-int launch_gpr_small(cudaStream_t s, const SmallArgs& a) {
-    static const int which = [] { const char* e = getenv("MFGP_SMALL_KERNEL"); return e ? atoi(e) : 5; }();
-    return which == 4 ? launch_gpr_small_v4(s, a) : launch_gpr_small_v5(s, a);
-}
-
 extern "C" {
 
 int mfgp_version(void) { return 100; }

@@ -1,18 +1,25 @@
-// gemm.cu -- batched fp64 GEMM for sm_100a on the FP64 tensor path.
+// gemm.cu -- batched fp64 GEMM for sm_100a on the FP64 tensor path, operand tiles fed by TMA.
 //
 // tcgen05.mma has no f64 kind, so the FP64 tensor path on Blackwell is the warp-level
-// mma.sync.m8n8k4.f64 (SASS: DMMA.8x8x4).  This kernel feeds it from a 4-stage cp.async
-// (LDGSTS, 16-byte, zero-filling) shared-memory pipeline with XOR-swizzled tiles so that the
-// 8-byte fragment loads of both operand layouts are bank-conflict free:
-//   * K-major operand (contiguous along k): tile [rows][16], 16-byte chunk c of row r stored at
-//     chunk c ^ (r & 7); an MMA row-fragment uses rows {2g + b} of a 16-row group so the four
-//     rows of a half-warp land in four different bank octets.
-//   * M-major operand (contiguous along m/n): tile [16][rows], chunk c of k-row k stored at
-//     chunk c ^ ((k & 3) << 1); an MMA fragment uses 8 consecutive rows.
+// mma.sync.m8n8k4.f64 (SASS: DMMA.8x8x4).  This kernel feeds it from a 4-stage shared-memory ring that the TMA unit
+// fills (cp.async.bulk.tensor, SASS UTMALDG) and mbarriers hand over: one elected thread arms the stage's barrier with
+// the byte count and issues the tile copies, the eight MMA warps wait on the barrier's phase.  No thread computes an
+// address or a bounds predicate for the operand stream: the tensor maps carry shapes and strides (incl. the strided
+// batch dimensions), out-of-range rows / k are zero-filled by the hardware, and the 128-byte swizzle of the tensor
+// map produces the bank-conflict-free layout the 8-byte fragment loads need:
+//   * K-major operand (contiguous along k): one box [rows][16 k] per stage; a row is 128 bytes and its 16-byte chunk c
+//     lands at chunk c ^ (row & 7); an MMA row-fragment uses rows {2g + b} of a 16-row group, so the four rows of a
+//     half-warp land in four different bank octets.
+//   * M-major operand (contiguous along m/n): rows / 16 boxes [16 k][16 m] per stage (2 KB each); inside a box k-row k is
+//     128 bytes and chunk c of it lands at c ^ (k & 7); an MMA fragment takes the rows {0-3, 8-11} or {4-7, 12-15} of a
+//     box (frag_row below), which makes the 16 lanes of a half-warp hit 16 distinct 8-byte bank pairs.
+//   Both layouts and the epilogue mapping are modelled on the CPU in tests/test_gemm_layout_model.py.
 // Warp tile 64x32 (128x128 CTA, 8 warps) or 32x32 (64x64 CTA, 4 warps): 12 (8) LDS.64 per
 // 32 (16) DMMA.  Triangular operands are expressed as per-tile k ranges (GemmKRange).
 #include "gemm.cuh"
 #include "common.cuh"
+
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 
 #include <cstdint>
 
@@ -40,49 +47,53 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-// ---- global -> shared tile copies ------------------------------------------------------------
-// K-major source: element (r, k) at g[(row0 + r) * ld + k]
-template <int ROWS, int NT>
-__device__ __forceinline__ void load_kmajor(uint32_t sbase, const double* __restrict__ g, long ld, int row0,
-                                            int nrows, int k0, int kend, int tid) {
-#pragma unroll
-    for (int it = 0; it < ROWS * 8 / NT; ++it) {
-        const int idx = tid + it * NT;
-        const int r = idx >> 3, c = idx & 7;
-        const int grow = row0 + r, gk = k0 + 2 * c;
-        int valid = (grow < nrows) ? (kend - gk) : 0;
-        valid = valid < 0 ? 0 : (valid > 2 ? 2 : valid);
-        const double* src = valid ? g + (long)grow * ld + gk : g;
-        cp_async16(sbase + r * 128 + ((c ^ (r & 7)) << 4), src, valid * 8);
-    }
+// ---- TMA / mbarrier primitives -------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
 }
-// M-major source: element (r, k) at g[k * ld + row0 + r]
-template <int ROWS, int NT>
-__device__ __forceinline__ void load_mmajor(uint32_t sbase, const double* __restrict__ g, long ld, int row0,
-                                            int nrows, int k0, int kend, int tid) {
-    constexpr int CPR = ROWS / 2;  // 16-byte chunks per k-row
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// 4-D tiled copy: coordinates (contiguous dimension, row dimension, batch, outer batch)
+__device__ __forceinline__ void tma_load(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(dst),
+                 "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
+// One stage of one operand.  K-major: a single box [ROWS][BK].  M-major: ROWS / 16 boxes [BK][16].
+template <bool KMAJOR, int ROWS>
+__device__ __forceinline__ void tma_operand(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int row0, int k0, int b1, int b2) {
+    if (KMAJOR) tma_load(dst, tm, bar, k0, row0, b1, b2);
+    else {
 #pragma unroll
-    for (int it = 0; it < BK * CPR / NT; ++it) {
-        const int idx = tid + it * NT;
-        const int k = idx / CPR, c = idx % CPR;
-        const int gk = k0 + k, gi = row0 + 2 * c;
-        int valid = (gk < kend) ? (nrows - gi) : 0;
-        valid = valid < 0 ? 0 : (valid > 2 ? 2 : valid);
-        const double* src = valid ? g + (long)gk * ld + gi : g;
-        cp_async16(sbase + k * (ROWS * 8) + ((c ^ ((k & 3) << 1)) << 4), src, valid * 8);
+        for (int b = 0; b < ROWS / 16; ++b) tma_load(dst + b * 2048, tm, bar, row0 + 16 * b, k0, b1, b2);
     }
 }
 
-// tile-local row of MMA row g (0..7) of fragment f inside a warp tile starting at w0
+// tile-local row of MMA row g (0..7) of fragment f inside a warp tile starting at w0 (a multiple of 32)
 template <bool KMAJOR>
 __device__ __forceinline__ int frag_row(int w0, int f, int g) {
-    return KMAJOR ? w0 + (f >> 1) * 16 + 2 * g + (f & 1) : w0 + f * 8 + g;
+    return KMAJOR ? w0 + (f >> 1) * 16 + 2 * g + (f & 1)
+                  : w0 + (f >> 1) * 16 + 8 * ((g >> 1) & 1) + 4 * (f & 1) + 2 * (g >> 2) + (g & 1);
 }
-// shared address (bytes, relative to tile base) of element (row, k)
+// shared address (bytes, relative to the 1024-byte aligned tile base) of element (row, k): the TMA 128-byte swizzle
 template <bool KMAJOR, int ROWS>
 __device__ __forceinline__ uint32_t frag_addr(int row, int k) {
     return KMAJOR ? (uint32_t)(row * 128 + (((k >> 1) ^ (row & 7)) << 4) + ((k & 1) << 3))
-                  : (uint32_t)(k * (ROWS * 8) + (((row >> 1) ^ ((k & 3) << 1)) << 4) + ((row & 1) << 3));
+                  : (uint32_t)((row >> 4) * 2048 + k * 128 + ((((row & 15) >> 1) ^ (k & 7)) << 4) + ((row & 1) << 3));
 }
 
 struct KernelArgs {
@@ -97,26 +108,27 @@ struct KernelArgs {
     int krange, lower_only, vec_ok;
     int batch;
     long strideA2, strideB2, strideC2;
+    int bA1, bA2, bB1, bB2;  // 1: the operand has that batch dimension in its tensor map (0: broadcast, coordinate 0)
 };
 
 template <int BM, int BN, int WM, int WN, bool TA, bool TB>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN == 128 * 128 ? 1 : 2)) dgemm_kernel(KernelArgs p) {
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN == 128 * 128 ? 1 : 2))
+    dgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, KernelArgs p) {
     constexpr int NWN = BN / WN;
     constexpr int NT = (BM / WM) * NWN * 32;
     constexpr int MT = WM / 8, NTL = WN / 8;
     constexpr bool A_KM = !TA, B_KM = TB;
     constexpr int A_BYTES = BM * BK * 8, B_BYTES = BN * BK * 8, STAGE_BYTES = A_BYTES + B_BYTES;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    __shared__ __align__(8) unsigned long long full_bar[STAGES];
 
     const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
     if (p.lower_only && j0 >= i0 + BM) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int wm0 = (warp / NWN) * WM, wn0 = (warp % NWN) * WN;
-    const long b1 = blockIdx.z % p.batch, b2 = blockIdx.z / p.batch;
-    const double* __restrict__ A = p.A + b1 * p.strideA + b2 * p.strideA2;
-    const double* __restrict__ B = p.B + b1 * p.strideB + b2 * p.strideB2;
-    double* __restrict__ C = p.C + b1 * p.strideC + b2 * p.strideC2;
+    const int b1 = blockIdx.z % p.batch, b2 = blockIdx.z / p.batch;
+    double* __restrict__ C = p.C + (long)b1 * p.strideC + (long)b2 * p.strideC2;
 
     int klo = 0, khi = p.K;
     switch (p.krange & 3) {
@@ -131,15 +143,27 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN == 128 * 
         case KR_HI_MINIJ: khi = min(khi, min(i0 + BM, j0 + BN)); break;
         default: break;
     }
+    // k ranges start and end on multiples of the tile sizes (or at K, beyond which the tensor map zero-fills), so whole
+    // BK-wide boxes are loaded and no partial-k predicate is needed
     const int nk = (khi > klo && p.alpha != 0.0) ? (khi - klo + BK - 1) / BK : 0;
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    // the 128-byte swizzle is a function of the shared-memory ADDRESS: tile bases must be 1024-byte aligned
+    const uint32_t sraw = (uint32_t)__cvta_generic_to_shared(smem_dyn);
+    const uint32_t sbase = (sraw + 1023u) & ~1023u;
+    unsigned char* smem_raw = smem_dyn + (sbase - sraw);
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(full_bar);
 
-    auto load_stage = [&](int stage, int k0) {
-        const uint32_t sa = sbase + stage * STAGE_BYTES, sb = sa + A_BYTES;
-        if (A_KM) load_kmajor<BM, NT>(sa, A, p.lda, i0, p.M, k0, khi, tid);
-        else load_mmajor<BM, NT>(sa, A, p.lda, i0, p.M, k0, khi, tid);
-        if (B_KM) load_kmajor<BN, NT>(sb, B, p.ldb, j0, p.N, k0, khi, tid);
-        else load_mmajor<BN, NT>(sb, B, p.ldb, j0, p.N, k0, khi, tid);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    auto load_stage = [&](int stage, int k0) {  // one elected thread: arm the barrier, issue the boxes
+        const uint32_t sa = sbase + stage * STAGE_BYTES, sb = sa + A_BYTES, bar = bar0 + 8 * stage;
+        mbar_expect_tx(bar, STAGE_BYTES);
+        tma_operand<A_KM, BM>(sa, &tmA, bar, i0, k0, p.bA1 ? b1 : 0, p.bA2 ? b2 : 0);
+        tma_operand<B_KM, BN>(sb, &tmB, bar, j0, k0, p.bB1 ? b1 : 0, p.bB2 ? b2 : 0);
     };
 
     double acc[MT][NTL][2];
@@ -149,10 +173,10 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN == 128 * 
 #pragma unroll
     for (int n = 0; n < NTL; ++n) bcol[n] = frag_row<B_KM>(wn0, n, g);
 
+    if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nk) load_stage(s, klo + s * BK);
-        cp_async_commit();
+        for (int s = 0; s < STAGES - 1; ++s)
+            if (s < nk) load_stage(s, klo + s * BK);
     }
 
 #pragma unroll
@@ -161,11 +185,11 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN == 128 * 
         for (int n = 0; n < NTL; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
 
     for (int it = 0; it < nk; ++it) {
-        cp_async_wait<STAGES - 2>();
+        // stage (it - 1) % STAGES was read in the previous iteration: once every warp is past this barrier it may be refilled
         __syncthreads();
         const int nxt = it + STAGES - 1;
-        if (nxt < nk) load_stage(nxt % STAGES, klo + nxt * BK);
-        cp_async_commit();
+        if (tid == 0 && nxt < nk) load_stage(nxt % STAGES, klo + nxt * BK);
+        mbar_wait(bar0 + 8 * (it % STAGES), (it / STAGES) & 1);  // the TMA bytes of stage `it` have landed
         const uint32_t sa = sbase + (it % STAGES) * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
@@ -181,7 +205,6 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN == 128 * 
                 for (int n = 0; n < NTL; ++n) dmma(acc[m][n][0], acc[m][n][1], af[m], bf[n]);
         }
     }
-    cp_async_wait<0>();
 
     // ---- epilogue through shared memory -----------------------------------------------------------
     // The accumulator fragments own 16-byte pieces scattered over 8 rows; reading/writing C straight from
@@ -233,7 +256,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN == 128 * 
             }
         } else {
 #pragma unroll
-            for (int n = 0; n < NTL; ++n) merge2(r, wn0 + n * 8 + 2 * t, acc[m][n][0], acc[m][n][1]);
+            for (int n = 0; n < NTL; ++n) merge2(r, frag_row<false>(wn0, n, 2 * t), acc[m][n][0], acc[m][n][1]);
         }
     }
     __syncthreads();
@@ -252,14 +275,52 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN == 128 * 
     }
 }
 
+// ---- tensor maps -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// Operand `base` with op-rows of extent `rows` (M or N) and contraction extent K.  kmajor: element (r, k) at base[r * ld + k];
+// else at base[k * ld + r].  Dimensions 2, 3: the two strided batch levels (extent 1 when the operand is broadcast).
+bool make_operand_map(CUtensorMap* tm, const double* base, bool kmajor, int rows, int K, long ld, int tile_rows, int nb1, long s1,
+                      int nb2, long s2) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    if (K < 1) K = 1;  // K == 0 (C = beta C): no box is ever requested, the map only has to be well formed
+    const cuuint64_t inner = kmajor ? (cuuint64_t)K : (cuuint64_t)rows, outer = kmajor ? (cuuint64_t)rows : (cuuint64_t)K;
+    const cuuint64_t dims[4] = {inner, outer, (cuuint64_t)(s1 ? nb1 : 1), (cuuint64_t)(s2 ? nb2 : 1)};
+    // strides of dimensions 1..3 in bytes (multiples of 16: ld and the batch strides are even)
+    const cuuint64_t one_matrix = (cuuint64_t)ld * 8 * outer;
+    const cuuint64_t strides[3] = {(cuuint64_t)ld * 8, s1 ? (cuuint64_t)s1 * 8 : one_matrix, s2 ? (cuuint64_t)s2 * 8 : one_matrix};
+    const cuuint32_t box[4] = {16, (cuuint32_t)(kmajor ? tile_rows : BK), 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int BM, int BN, int WM, int WN, bool TA, bool TB>
 int launch_cfg(cudaStream_t s, const GemmArgs& a, const KernelArgs& ka) {
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
-    constexpr int SMEM = STAGES * (BM + BN) * BK * 8;
+    constexpr int SMEM = STAGES * (BM + BN) * BK * 8 + 1024;  // + alignment slack for the 1024-byte swizzle atoms
     static SmemOptIn optin;
     if (!optin.ensure(dgemm_kernel<BM, BN, WM, WN, TA, TB>, SMEM)) return -2;
+    CUtensorMap tmA, tmB;
+    if (!make_operand_map(&tmA, a.A, !TA, a.M, a.K, a.lda, BM, a.batch, a.strideA, a.batch2, a.strideA2) ||
+        !make_operand_map(&tmB, a.B, TB, a.N, a.K, a.ldb, BN, a.batch, a.strideB, a.batch2, a.strideB2))
+        return -3;
     dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, a.batch * a.batch2);
-    dgemm_kernel<BM, BN, WM, WN, TA, TB><<<grid, NT, SMEM, s>>>(ka);
+    dgemm_kernel<BM, BN, WM, WN, TA, TB><<<grid, NT, SMEM, s>>>(tmA, tmB, ka);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -284,6 +345,7 @@ int launch_gemm(cudaStream_t s, const GemmArgs& a) {
     ka.C = a.C; ka.ldc = a.ldc; ka.strideC = a.strideC;
     ka.krange = a.krange; ka.lower_only = a.lower_only;
     ka.batch = a.batch; ka.strideA2 = a.strideA2; ka.strideB2 = a.strideB2; ka.strideC2 = a.strideC2;
+    ka.bA1 = a.strideA != 0; ka.bA2 = a.strideA2 != 0; ka.bB1 = a.strideB != 0; ka.bB2 = a.strideB2 != 0;
     ka.vec_ok = al16(a.C) && !(a.ldc & 1) && !(a.strideC & 1) && !(a.strideC2 & 1);
     // tile config: 0 = 128x128 (1 CTA/SM; the only one safe for the in-place panel solve), 1 = 64x64,
     // 2 = 128x64 (2 CTAs/SM: one CTA's prologue/epilogue hides behind the other's main loop) -- the default.

@@ -23,6 +23,4 @@ struct SmallArgs {
     double* scratch;      // v4: K^L of every problem in flight (L2-resident), filled by the launcher
 };
 int launch_gpr_small_v4(cudaStream_t s, const SmallArgs& a);  // persistent grid, one warp per problem, 12 warps per SM
-int launch_gpr_small_v5(cudaStream_t s, const SmallArgs& a);  // persistent grid, two warps per problem, 24 warps per SM
-// the K6 kernel in use (MFGP_SMALL_KERNEL=4 selects v4 for A/B measurements)
-int launch_gpr_small(cudaStream_t s, const SmallArgs& a);
+inline int launch_gpr_small(cudaStream_t s, const SmallArgs& a) { return launch_gpr_small_v4(s, a); }

@@ -1,5 +1,5 @@
-"""CPU model of the DMMA GEMM kernel's data movement (csrc/gemm.cu): swizzled cp.async tile
-layout -> fragment addresses -> m8n8k4 semantics -> epilogue mapping.  Catches index bugs
+"""CPU model of the DMMA GEMM kernel's data movement (csrc/gemm.cu): TMA boxes with the 128-byte swizzle
+-> fragment addresses -> m8n8k4 semantics -> epilogue mapping.  Catches index bugs
 without a GPU and proves the shared-memory reads are bank-conflict free."""
 import itertools
 
@@ -10,35 +10,42 @@ BK = 16
 
 
 def frag_row(kmajor, w0, f, g):
-    return w0 + (f >> 1) * 16 + 2 * g + (f & 1) if kmajor else w0 + f * 8 + g
+    if kmajor:
+        return w0 + (f >> 1) * 16 + 2 * g + (f & 1)
+    return w0 + (f >> 1) * 16 + 8 * ((g >> 1) & 1) + 4 * (f & 1) + 2 * (g >> 2) + (g & 1)
 
 
 def frag_addr(kmajor, rows, row, k):
     if kmajor:
         return row * 128 + (((k >> 1) ^ (row & 7)) << 4) + ((k & 1) << 3)
-    return k * (rows * 8) + (((row >> 1) ^ ((k & 3) << 1)) << 4) + ((row & 1) << 3)
+    return (row >> 4) * 2048 + k * 128 + ((((row & 15) >> 1) ^ (k & 7)) << 4) + ((row & 1) << 3)
+
+
+def swizzle_128b(addr):
+    """CU_TENSOR_MAP_SWIZZLE_128B: the 16-byte chunk index (address bits 4-6) is XORed with address bits 7-9; the pattern
+    repeats every 1024 bytes, which is why the tile bases are 1024-byte aligned."""
+    return addr ^ (((addr >> 7) & 7) << 4)
+
+
+def tma_box(smem, dst, G, c_inner, c_outer, n_inner, n_outer, inner_is_k, box_outer):
+    """One cp.async.bulk.tensor box [box_outer][16 doubles] written densely at `dst` (bytes) and swizzled; coordinates
+    outside the tensor (n_inner x n_outer) are zero-filled by the hardware."""
+    for o in range(box_outer):
+        for i in range(16):
+            ci, co = c_inner + i, c_outer + o
+            inside = ci < n_inner and co < n_outer
+            v = (G(co, ci) if inner_is_k else G(ci, co)) if inside else 0.0
+            smem[swizzle_128b(dst + o * 128 + i * 8) // 8] = v
 
 
 def load_tile(kmajor, rows, G, ld_is_k, row0, nrows, k0, kend):
-    """returns smem as array of doubles indexed by byte_addr // 8. G(r, k) global accessor."""
+    """returns smem as array of doubles indexed by byte_addr // 8. G(r, k) global accessor; kend = extent of k."""
     smem = np.full(rows * BK, np.nan)
     if kmajor:
-        for idx in range(rows * 8):
-            r, c = idx >> 3, idx & 7
-            grow, gk = row0 + r, k0 + 2 * c
-            valid = max(0, min(2, kend - gk)) if grow < nrows else 0
-            dst = r * 128 + ((c ^ (r & 7)) << 4)
-            for e in range(2):
-                smem[dst // 8 + e] = G(grow, gk + e) if e < valid else 0.0
+        tma_box(smem, 0, G, k0, row0, kend, nrows, True, rows)
     else:
-        cpr = rows // 2
-        for idx in range(BK * cpr):
-            k, c = idx // cpr, idx % cpr
-            gk, gi = k0 + k, row0 + 2 * c
-            valid = max(0, min(2, nrows - gi)) if gk < kend else 0
-            dst = k * (rows * 8) + ((c ^ ((k & 3) << 1)) << 4)
-            for e in range(2):
-                smem[dst // 8 + e] = G(gi + e, gk) if e < valid else 0.0
+        for b in range(rows // 16):
+            tma_box(smem, b * 2048, G, row0 + 16 * b, k0, nrows, kend, False, BK)
     assert not np.isnan(smem).any()
     return smem
 
@@ -100,7 +107,7 @@ def run_tile(BM, BN, WM, WN, TA, TB, A, B, M, N, K, i0, j0):
                         store2(i, j + 2, acc[warp, lane, m, 2 * q, 1], acc[warp, lane, m, 2 * q + 1, 1])
                 else:
                     for n in range(NTL):
-                        store2(i, j0 + wn0 + n * 8 + 2 * t, acc[warp, lane, m, n, 0], acc[warp, lane, m, n, 1])
+                        store2(i, j0 + frag_row(False, wn0, n, 2 * t), acc[warp, lane, m, n, 0], acc[warp, lane, m, n, 1])
     return out
 
 
