@@ -314,9 +314,9 @@ int launch_potrf(cudaStream_t s, const CholArgs& a) {
         int v = e ? atoi(e) : 0;
         return v < NB ? 0 : (v / NB) * NB;
     }();
-    // measured (highest-priority panel stream): N = 8192: 256 -> 18.1, 512 -> 17.1 TFLOP/s; N = 16 384: 256 -> 26.4, 512 -> 26.8;
-    // N = 32 768: 512 -> 29.8
-    const int OB = OB_env ? OB_env : (N <= 12288 ? 2 * NB : 4 * NB);
+    // measured with the TMA-fed GEMM (profiles/r02_potrf_outer_block.log): N = 8192: 128 -> 18.0, 256 -> 19.2, 384 -> 18.6 TFLOP/s;
+    // N = 16 384: 256 -> 27.7, 384 -> 28.6, 512 -> 29.0, 768 -> 28.9; N = 32 768: 512 -> 32.6, 768 -> 33.2, 1024 -> 33.4
+    const int OB = OB_env ? OB_env : (N <= 12288 ? 2 * NB : (N <= 24576 ? 4 * NB : 8 * NB));
     // Look-ahead: the latency-bound chain  diag -> panel -> inner update -> diag -> panel  runs on the aux stream and
     // overlaps the FP64-bound trailing update of the previous outer step; the main stream hands over the next
     // OB columns early.

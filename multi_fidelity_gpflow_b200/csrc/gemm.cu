@@ -22,6 +22,7 @@
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 
 #include <cstdint>
+#include <cstdlib>
 
 namespace {
 
@@ -350,10 +351,16 @@ int launch_gemm(cudaStream_t s, const GemmArgs& a) {
     // tile config: 0 = 128x128 (1 CTA/SM; the only one safe for the in-place panel solve), 1 = 64x64,
     // 2 = 128x64 (2 CTAs/SM: one CTA's prologue/epilogue hides behind the other's main loop) -- the default.
     int cfg;
+    static const int cfg_env = [] { const char* e = getenv("MFGP_GEMM_CFG"); return e ? atoi(e) : -1; }();  // experiments only
     if (a.small_tiles >= 0) cfg = a.small_tiles;
+    else if (cfg_env >= 0) cfg = cfg_env;
     else {
+        // 64x64 tiles when the grid would be small, or when 128-row tiles would pad M by > 12 % more than 64-row tiles do:
+        // M = 300 (the SVGP inducing-point count) is 384 in 128-row tiles but 320 in 64-row tiles -- measured on the Goku
+        // single-bin SVGP step: 7.93 -> 7.03 ms (profiles/r02_svgp_tile_config.log)
         const long ctas = (long)((a.M + 127) / 128) * ((a.N + 63) / 64) * a.batch * a.batch2;
-        cfg = ctas < 2 * 148 ? 1 : 2;
+        const double pad128 = (double)((a.M + 127) / 128 * 128) / a.M, pad64 = (double)((a.M + 63) / 64 * 64) / a.M;
+        cfg = (ctas < 2 * 148 || pad128 > 1.12 * pad64) ? 1 : 2;
     }
     if (!a.transA && !a.transB) return launch_t<false, false>(s, a, ka, cfg);
     if (!a.transA && a.transB) return launch_t<false, true>(s, a, ka, cfg);
