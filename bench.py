@@ -367,7 +367,7 @@ def leg_exact_gp(cx, peak):
 
     single = single_g = None
     if cx.rank == 0:  # the single-GPU answer: the measurement at world 1, the in-run reference at world > 1
-        h.gpr_nlml(X[:2048], Y[:2048], theta, noise)  # warm the pool / attributes
+        h.gpr_nlml(X, Y, theta, noise)  # warm-up at full size: the stream-ordered pool grows to its 17 GB working set once
         t0 = time.perf_counter()
         single = h.gpr_nlml(X, Y, theta, noise)
         t1 = time.perf_counter()
@@ -579,7 +579,7 @@ def run_mine(args):
             "dtype": "f64", "data": DATA, "config": config(R, extra),
             "roofline": {"bound": "tensor", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "gpr_small_v4_kernel<7,5>",
+                         "kernel": "gpr_small_v4_kernel<7,5>",  # the only K6 kernel in libmfgp.so (csrc/gpr_small_v4.cu)
                          "peak_source": "measured live: FP64 pipe microbenchmark (DMMA m8n8k4 / DFMA), "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "alg_flops_per_bin": ALG_FLOPS_PER_BIN, "alg_io_bytes": nprob * (13 + 1 + 1 + 14) * 8,

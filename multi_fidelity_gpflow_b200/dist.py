@@ -138,7 +138,7 @@ class SvgpDeviceOps:
 
 
 def dp_svgp_adam(handle_or_ops, X, Y, shape, u, mask, lr_t, beta1, beta2, eps=1e-7, num_data=None, kl_mult=1.0,
-                 group=None, timing=None):
+                 group=None, timing=None, use_graph=None):
     """len(lr_t) data-parallel Adam steps.  Every rank passes the same GLOBAL (mini)batch X [B, d+1], Y, the same flat
     unconstrained parameter vector `u` (layout of mfgp_svgp_adam), trainable mask and per-step factors `lr_t`
     (optimizers.adam_step_factors); rank r evaluates rows shard_range(B, r, world).
@@ -146,7 +146,10 @@ def dp_svgp_adam(handle_or_ops, X, Y, shape, u, mask, lr_t, beta1, beta2, eps=1e
     shape: dict(L, M, P, d, has_W, hetero, masked, lik_per_output, lik_lower).
     Returns (u_final, loss_hist, kl_hist) as NumPy arrays, identical on every rank (same reduced gradient, same update).
     timing (optional dict): receives 'ms_per_step' measured with device events around the loop (max over ranks is the
-    caller's job)."""
+    caller's job).
+    use_graph (default: on CUDA when there are more than 3 steps): the step -- ~60 kernel launches plus the NCCL all-reduce --
+    is launch-latency bound for the reference's model sizes, so after two eager steps ONE step is captured as a CUDA graph
+    (the step counter and the per-step factors live on the device, so the same graph serves every step) and replayed."""
     import torch
 
     dist = _dist()
@@ -180,12 +183,36 @@ def dp_svgp_adam(handle_or_ops, X, Y, shape, u, mask, lr_t, beta1, beta2, eps=1e
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier(group=group)
         e0.record()
-    for _ in range(nsteps):
+    def one_step():
         ops.constrain(cfg, has_W, ud, c)
         ops.elbo_grad_flat(cfg, Xd, Yd, has_W, c, world, eg)
         if world > 1:
             dist.all_reduce(eg, op=dist.ReduceOp.SUM, group=group)  # in place on the buffer the kernels wrote
         ops.adam_update(cfg, has_W, ud, md, vd, mk, c, eg, lrd, step, beta1, beta2, eps, loss_h, kl_h, scratch)
+
+    if use_graph is None:
+        use_graph = dev.type == "cuda" and nsteps > 3
+    done = 0
+    if use_graph:
+        for _ in range(2):  # eager: first-call attribute opt-ins, pool growth, NCCL channel set-up
+            one_step()
+        graph = torch.cuda.CUDAGraph()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            if hasattr(ops, "h"):
+                ops.h.set_stream(side.cuda_stream)
+            with torch.cuda.graph(graph, stream=side, capture_error_mode="relaxed"):
+                one_step()  # recorded, not executed
+        cur.wait_stream(side)
+        if hasattr(ops, "h"):
+            ops.h.set_stream(cur.cuda_stream)
+        for _ in range(2, nsteps):
+            graph.replay()
+        done = nsteps
+    for _ in range(done, nsteps):
+        one_step()
     if use_events:
         e1.record()
     if hasattr(ops, "end"):
