@@ -341,6 +341,37 @@ def leg_svgp_step(cx, peak):
             "B": B, "ms": dt * 1e3, "alg_flops": flops}
 
 
+def leg_goku_per_bin(cx, peak):
+    """BASELINE config 2 on the Goku arrays (C2g): one linear MF GPR per k-bin, 64 bins x N = 1164, d = 10, NLML + gradient
+    through the batched blocked path (N > 64: K1 -> batched potrf / trtri -> DMMA GEMMs -> K5), host buffers."""
+    from multi_fidelity_gpflow_b200.data import PowerSpecs
+
+    ps = PowerSpecs().read_from_npz(os.path.join(ROOT, "tests", "golden", "goku.npz"))
+    X, Y = ps.training_arrays()
+    N, P = Y.shape
+    d = X.shape[1] - 1
+    rng = np.random.default_rng(7)
+    th = np.exp(0.2 * rng.standard_normal((P, 2 * d + 3)))
+    nz = np.full(P, 1e-3)
+    h = cx.h
+    h.set_stream(None)
+    h.set_async(False)
+    nl, gr = h.gpr_batched_nlml_grad(X, Y, th, nz)  # warm-up
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        nl, gr = h.gpr_batched_nlml_grad(X, Y, th, nz)
+    dt = (time.perf_counter() - t0) / reps
+    # verify bin 0 against the single-problem path (same building blocks, different batching)
+    v0, g0 = h.gpr_nlml_grad(X, np.ascontiguousarray(Y[:, :1]), th[0], 1e-3)
+    assert abs(v0 - nl[0]) < 1e-10 * abs(v0) and np.max(np.abs(g0 - gr[0])) < 1e-8 * np.max(np.abs(g0))
+    flops = P * (float(N) ** 3 + 4.0 * N * N)
+    h.set_stream(cx.stream.cuda_stream)
+    return {"kernel": "batched exact GPR, 64 bins x N=1164 (K1 + batched potrf/trtri + DMMA GEMMs + K5)", "bound": "tensor",
+            "achieved": flops / dt / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": flops / dt / peak, "bins": P, "N": N,
+            "ms": dt * 1e3, "evals_per_s": 1.0 / dt, "alg_flops": flops}
+
+
 def leg_exact_gp(cx, peak):
     """BASELINE config 5: 32 768-point two-fidelity exact GP, NLML and NLML + gradient.  world 1: the single-GPU path.
     world > 1: 2-D block-cyclic distributed Cholesky (panel broadcasts over NVLink), asserted against rank 0's single-GPU
@@ -381,7 +412,12 @@ def leg_exact_gp(cx, peak):
                              "note": "host wall time of the C-ABI call with host buffers (H2D of X, Y inside)"}
         torch.cuda.empty_cache()
     if cx.world > 1:
+        from multi_fidelity_gpflow_b200.dist_chol import GpuOps
+
         nb = cx.args.dist_nb
+        ops = GpuOps(h)
+        ops.stats = {}
+        h._dist_ops = ops
         t_v, v = timed(lambda: distributed_gpr_nlml(h, X, Y, theta, noise, nbd=nb), 3)
         t_g, (v2, g2) = timed(lambda: distributed_gpr_nlml(h, X, Y, theta, noise, nbd=nb, want_grad=True), 2)
         ok = True
@@ -390,6 +426,9 @@ def leg_exact_gp(cx, peak):
             out["dist_vs_single_gpu"] = {"nlml_rel_err": ev, "grad_rel_err": eg}
             ok = ev < 1e-9 and eg < 1e-7 and abs(v2 - v) <= 1e-12 * abs(v)
         P, Q = process_grid(cx.world)
+        out["critical_path_messages"] = ops.stats.get("critical_messages")
+        if getattr(ops, "p2p_error", None):
+            out["peer_memory_unavailable"] = ops.p2p_error[:200]
         out.update({"grid": [P, Q], "block": nb, "dist_potrf_n32768_ms": t_v * 1e3,
                     "dist_potrf_n32768_tflops": N**3 / 3 / t_v / 1e12,
                     "dist_potrf_n32768_frac_of_N_x_peak": N**3 / 3 / t_v / (cx.world * peak),
@@ -430,7 +469,7 @@ def leg_dp_svgp(cx):
     mk = lambda: copy.deepcopy(base)
     out = {"L": 15, "M": 300, "P": P,
            "grad_doubles": int(15 * (2 * d + 3) + 300 * (d + 1) + P * 15 + 300 * 15 + 15 * 300 * 300 + 1)}
-    steps = 12
+    steps = 42  # 2 eager + 40 replays of the captured step
     solo = dist.new_group([0]) if cx.world > 1 else None
     for B in (X.shape[0], 256):
         data = (X[:B], Y[:B])
@@ -439,6 +478,7 @@ def leg_dp_svgp(cx):
         t = {}
         m.optimize_data_parallel(data, max_iters=steps, initial_lr=0.005, timing=t)
         out[f"dp_svgp_ms_per_step_B{B}"] = cx.max_over_ranks(t["ms_per_step"])
+        out[f"dp_svgp_graph_setup_ms_B{B}"] = t.get("setup_ms")
         assert np.all(np.isfinite(m.loss_history))
         if cx.world > 1 and cx.rank == 0:  # same trajectory as one rank (sub-group of rank 0), checked in the run
             r = mk()
@@ -553,6 +593,7 @@ def run_mine(args):
                      "potrf_n16384_residual_rel": pr["residual_rel"], "fp64_peak_tflops_measured": peak / 1e12}
             roof_extra.extend(leg_cov(cx, hbm_peak))
             roof_extra.append(leg_svgp_step(cx, peak))
+            roof_extra.append(leg_goku_per_bin(cx, peak))
         multi["exact_gp_n32768"] = leg_exact_gp(cx, peak)
         multi["dp_svgp_goku_latent"] = leg_dp_svgp(cx)
         if world > 1:

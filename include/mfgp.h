@@ -202,6 +202,14 @@ int mfgp_gemm(mfgp_handle* h, char transa, char transb, int m, int n, int k, dou
 int mfgp_potrf(mfgp_handle* h, double* A, int N, long lda);
 /* Winv [N, N] = inv(L) for the lower factor produced by mfgp_potrf. */
 int mfgp_potrf_inv(mfgp_handle* h, double* A, int N, long lda, double* Winv, long ldw);
+/* One-to-many store: `count` doubles (even, 16-byte aligned) from src into ndst <= MFGP_PEER_MAX destination buffers in ONE
+ * kernel on the handle's stream.  The destinations are device pointers valid in this process -- buffers of PEER GPUs mapped
+ * over NVLink (symmetric memory, CUDA IPC) or local ones.  Used for the critical-path messages of the distributed Cholesky
+ * (dist_chol.py: inv(L_kk) and the early block go to all peers by direct stores instead of an NCCL broadcast); the caller
+ * orders the stores against the receivers with its own signal (never synchronises). */
+#define MFGP_PEER_MAX 8
+int mfgp_peer_store(mfgp_handle* h, const double* src, long count, int ndst, double* const* dsts);
+
 /* FP64 pipe microbenchmarks (bench.py: measured FP64 peak).  kind 0: DFMA, 1: DMMA m8n8k4, 2: both interleaved with equal
  * pipe time (tells whether the two share one datapath: same FLOP/s as either alone, or not: up to twice).
  * Returns achieved FLOP/s in *flops. */

@@ -65,6 +65,7 @@ def _load():
         "mfgp_gemm": ([vp, C.c_char, C.c_char, i, i, i, d, vp, l, vp, l, d, vp, l], i),
         "mfgp_potrf": ([vp, vp, i, l], i),
         "mfgp_potrf_inv": ([vp, vp, i, l, vp, l], i),
+        "mfgp_peer_store": ([vp, vp, l, i, C.POINTER(vp)], i),
         "mfgp_fp64_peak": ([vp, i, i, C.POINTER(d)], i),
     }
     for name, (args, res) in sig.items():
@@ -81,7 +82,7 @@ EXPORTED_SYMBOLS = [
     "mfgp_gpr_predict", "mfgp_gpr_batched_nlml_grad", "mfgp_gpr_batched_adam",
     "mfgp_graph_nparams", "mfgp_graph_cov", "mfgp_graph_cov_diag", "mfgp_graph_gpr_nlml_grad", "mfgp_svgp_elbo_grad", "mfgp_svgp_elbo_grad_v", "mfgp_svgp_predict", "mfgp_svgp_adam",
     "mfgp_svgp_flat_size", "mfgp_svgp_constrain", "mfgp_svgp_elbo_grad_flat", "mfgp_svgp_adam_update", "mfgp_gemm",
-    "mfgp_potrf", "mfgp_potrf_inv", "mfgp_fp64_peak",
+    "mfgp_potrf", "mfgp_potrf_inv", "mfgp_peer_store", "mfgp_fp64_peak",
 ]
 
 
@@ -444,6 +445,11 @@ class Handle:
 
     def potrf_device(self, A_dev, N, lda):
         self._check(_lib.mfgp_potrf(self._h, _ptr(A_dev), N, lda), "mfgp_potrf")
+
+    def peer_store(self, src, dst_ptrs, count):
+        """One kernel: `count` doubles from `src` into every raw device address in `dst_ptrs` (peer GPUs' mapped buffers or local)."""
+        arr = (C.c_void_p * len(dst_ptrs))(*[C.c_void_p(int(p)) for p in dst_ptrs])
+        self._check(_lib.mfgp_peer_store(self._h, _ptr(src), int(count), len(dst_ptrs), arr), "mfgp_peer_store")
 
     def fp64_peak(self, kind: int, iters: int = 20000) -> float:
         out = C.c_double(0.0)

@@ -508,6 +508,43 @@ int mfgp_potrf_inv(mfgp_handle* h, double* A, int N, long lda, double* Winv, lon
     return potrf_common(h, A, N, lda, Winv, ldw);
 }
 
+// ---- one-to-many store over peer memory ----------------------------------------------------------------
+// The critical-path messages of the distributed Cholesky (inv(L_kk) and the early block (k+1, k), nb x nb doubles) go to
+// every other GPU of the box.  With the peers' buffers mapped into this process (symmetric memory over NVLink / NVSwitch)
+// that is ONE kernel: each 16-byte piece of the source is read once and stored to every destination, so the transfers to
+// the peers run concurrently on all NVLink lanes and never queue behind the bulk panel broadcasts of the NCCL stream.
+struct PeerDsts {
+    double* p[MFGP_PEER_MAX];
+};
+__global__ void __launch_bounds__(256) peer_store_kernel(const double2* __restrict__ src, long n2, int ndst, PeerDsts d) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long)gridDim.x * blockDim.x) {
+        const double2 v = src[i];
+#pragma unroll
+        for (int k = 0; k < MFGP_PEER_MAX; ++k)
+            if (k < ndst) reinterpret_cast<double2*>(d.p[k])[i] = v;
+    }
+}
+
+int mfgp_peer_store(mfgp_handle* h, const double* src, long count, int ndst, double* const* dsts) {
+    CHECK_H(h);
+    if (!src || !dsts || count < 0 || (count & 1) || ndst < 0 || ndst > MFGP_PEER_MAX || (reinterpret_cast<size_t>(src) & 15))
+        return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_peer_store: bad argument (even count, 16-byte aligned, <= %d destinations)", MFGP_PEER_MAX);
+    if (ndst == 0 || count == 0) return 0;
+    cudaSetDevice(h->device);
+    PeerDsts d{};
+    for (int k = 0; k < ndst; ++k) {
+        if (!dsts[k] || (reinterpret_cast<size_t>(dsts[k]) & 15)) return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_peer_store: destination %d unaligned", k);
+        d.p[k] = dsts[k];
+    }
+    const long n2 = count / 2;
+    long blocks = (n2 + 255) / 256;
+    const long cap = (long)h->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    peer_store_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(reinterpret_cast<const double2*>(src), n2, ndst, d);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
 // ---- FP64 pipe microbenchmarks ---------------------------------------------------------------
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
     double a[16];

@@ -145,8 +145,9 @@ def dp_svgp_adam(handle_or_ops, X, Y, shape, u, mask, lr_t, beta1, beta2, eps=1e
 
     shape: dict(L, M, P, d, has_W, hetero, masked, lik_per_output, lik_lower).
     Returns (u_final, loss_hist, kl_hist) as NumPy arrays, identical on every rank (same reduced gradient, same update).
-    timing (optional dict): receives 'ms_per_step' measured with device events around the loop (max over ranks is the
-    caller's job).
+    timing (optional dict): receives 'ms_per_step' measured with device events around the steady-state steps (the replayed
+    steps when a graph is used, else the whole loop; max over ranks is the caller's job) and 'setup_ms', the wall time of the
+    two eager steps + capture + instantiation that a graph costs once per call.
     use_graph (default: on CUDA when there are more than 3 steps): the step -- ~60 kernel launches plus the NCCL all-reduce --
     is launch-latency bound for the reference's model sizes, so after two eager steps ONE step is captured as a CUDA graph
     (the step counter and the per-step factors live on the device, so the same graph serves every step) and replayed."""
@@ -179,9 +180,13 @@ def dp_svgp_adam(handle_or_ops, X, Y, shape, u, mask, lr_t, beta1, beta2, eps=1e
     if hasattr(ops, "begin"):
         ops.begin()
     use_events = timing is not None and dev.type == "cuda"
+    timed_steps = nsteps
     if use_events:
+        import time as _time
+
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier(group=group)
+        t_setup = _time.perf_counter()
         e0.record()
     def one_step():
         ops.constrain(cfg, has_W, ud, c)
@@ -208,6 +213,12 @@ def dp_svgp_adam(handle_or_ops, X, Y, shape, u, mask, lr_t, beta1, beta2, eps=1e
         cur.wait_stream(side)
         if hasattr(ops, "h"):
             ops.h.set_stream(cur.cuda_stream)
+        if use_events:  # steady state = the replayed steps
+            torch.cuda.current_stream().synchronize()
+            timing["setup_ms"] = (_time.perf_counter() - t_setup) * 1e3
+            dist.barrier(group=group)
+            e0.record()
+            timed_steps = nsteps - 2
         for _ in range(2, nsteps):
             graph.replay()
         done = nsteps
@@ -218,5 +229,6 @@ def dp_svgp_adam(handle_or_ops, X, Y, shape, u, mask, lr_t, beta1, beta2, eps=1e
     if hasattr(ops, "end"):
         ops.end()
     if use_events:
-        timing["ms_per_step"] = e0.elapsed_time(e1) / max(nsteps, 1)
+        timing["ms_per_step"] = e0.elapsed_time(e1) / max(timed_steps, 1)
+        timing["graph"] = bool(use_graph)
     return ud.cpu().numpy(), loss_h.cpu().numpy(), kl_h.cpu().numpy()

@@ -100,6 +100,39 @@ class GpuOps:
         if info:
             raise self._lib.NotPositiveDefiniteError(f"distributed potrf: pivot {info} of a diagonal block not positive")
 
+    # -- NVLink peer memory for the critical-path messages --------------------------------------------------
+    def peer_buffers(self, count, nb, group):
+        """`count` symmetric nb x nb blocks (torch symmetric memory: every rank's allocation is mapped into every peer
+        over NVLink).  Returns (local [count, nb, nb], handle, [peer views]) or None when peer memory is unavailable."""
+        if os.environ.get("MFGP_DIST_P2P") == "0":
+            return None
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+
+            pg = group if group is not None else dist.group.WORLD
+            local = symm.empty((count, nb, nb), dtype=self.torch.float64, device=self.device)
+            hdl = symm.rendezvous(local, pg)
+            world = dist.get_world_size(pg)
+            peers = [hdl.get_buffer(r, (count, nb, nb), self.torch.float64) for r in range(world)]
+            return local, hdl, peers
+        except Exception as e:  # no P2P / unsupported build: the NCCL broadcasts remain (reported, not silent)
+            self.p2p_error = repr(e)
+            return None
+
+    def peer_publish(self, hdl, peers, local_block, k, me, channel):
+        """Owner side: store block k into every peer's copy with direct NVLink writes (ONE kernel of the library for up to
+        8 destinations, mfgp_peer_store), then raise every peer's signal."""
+        others = [r for r in range(len(peers)) if r != me]
+        for o in range(0, len(others), 8):
+            grp = others[o:o + 8]
+            self.h.peer_store(local_block, [peers[r][k].data_ptr() for r in grp], local_block.numel())
+        for r in others:
+            hdl.put_signal(r, channel, 30000)
+
+    def peer_wait(self, hdl, src, channel):
+        hdl.wait_signal(src, channel, 30000)
+
     # -- block arithmetic -------------------------------------------------------------------------------
     def cov(self, Xa, Xb, theta, out):
         ptr = self._vptr
@@ -220,6 +253,15 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
         cache["piece"] = torch.empty(((nblk + P - 1) // P) * nb, nb, dtype=torch.float64, device=dev)
         cache["Rloc"] = torch.empty(max(len(R), 1) * nb, nb, dtype=torch.float64, device=dev)
         cache["Xr"] = torch.empty(max(len(R), 1) * nb, d + 1, dtype=torch.float64, device=dev)
+        # Critical-path messages (inv(L_kk) and the early block (k+1, k)): one symmetric slot PER STEP (2 x nblk x nb^2 doubles
+        # -- 0.5 GB at N = 32 768, nothing next to 180 GB of HBM), so a slot is never reused inside a factorisation and the
+        # owner can store it into every peer without asking whether the previous tenant has been consumed.
+        cache["p2p"] = None
+        if world > 1 and hasattr(ops, "peer_buffers"):
+            pw = ops.peer_buffers(nblk, nb, group)
+            pb = ops.peer_buffers(nblk, nb, group) if pw is not None else None
+            if pw is not None and pb is not None:
+                cache["p2p"] = {"W": pw, "B": pb}
         try:
             ops._dist_chol_ws = cache
         except AttributeError:
@@ -266,6 +308,11 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
     logdet = torch.zeros(1, dtype=torch.float64, device=dev)
     quad = torch.zeros(1, dtype=torch.float64, device=dev)
     pans, Wks, blks, piece, Rloc = cache["pans"], cache["Wks"], cache["blks"], cache["piece"], cache["Rloc"]
+    p2p = cache.get("p2p") if lookahead else None
+    if isinstance(getattr(ops, "stats", None), dict):
+        ops.stats["critical_messages"] = "nvlink peer stores + signals" if p2p is not None else "nccl broadcast"
+    W_of = (lambda k: p2p["W"][0][k]) if p2p is not None else (lambda k: Wks[k % 2])
+    blk_of = (lambda k: p2p["B"][0][k]) if p2p is not None else (lambda k: blks[k % 2])
     ak = torch.zeros(nb, 2, dtype=torch.float64, device=dev)
     a_all = torch.zeros(N, 2, dtype=torch.float64, device=dev) if want_grad else None
     ev_W, ev_blk, ev_pan, ev_la, ev_done = {}, {}, {}, {}, {-1: ev_main}
@@ -304,7 +351,7 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
         """Critical path of step k: factor the diagonal block, broadcast its inverse, solve + broadcast the ONE block
         (k+1, k) and finish the next diagonal block, so that potrf(k+1) never waits for the bulk of panel k."""
         buf = k % 2
-        Wk, blk = Wks[buf], blks[buf]
+        Wk, blk = W_of(k), blk_of(k)
         ops.wait(s_crit, ev_done.get(k - 2))  # W/blk buffers free; main's updates of the blocks touched below are complete
         with _Phase("diag_potrf_inv"):
             if rank == rank_of(k, k):
@@ -312,7 +359,13 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
                 ops.potrf_inv(A[:nb], Wk)
                 logdet.add_(torch.log(A[:nb].diagonal()).sum())
         with _Phase("bcast_W"):
-            dist.broadcast(Wk, src=rank_of(k, k), group=crit_group)
+            if p2p is not None:  # direct NVLink stores + signal: never queues behind the panel broadcasts
+                if rank == rank_of(k, k):
+                    ops.peer_publish(p2p["W"][1], p2p["W"][2], Wk, k, rank, 0)
+                else:
+                    ops.peer_wait(p2p["W"][1], rank_of(k, k), 0)
+            else:
+                dist.broadcast(Wk, src=rank_of(k, k), group=crit_group)
         ev_W[k] = ops.record(s_crit)
         if k + 1 >= nblk:
             return
@@ -323,7 +376,13 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
                 o = local_off(k, k + 1)
                 ops.gemm(False, True, nb, nb, nb, 1.0, cols[k][o:o + nb], Wk, 0.0, blk)
                 cols[k][o:o + nb].copy_(blk)
-            dist.broadcast(blk, src=src, group=crit_group)
+            if p2p is not None:
+                if rank == src:
+                    ops.peer_publish(p2p["B"][1], p2p["B"][2], blk, k, rank, 1)
+                else:
+                    ops.peer_wait(p2p["B"][1], src, 1)
+            else:
+                dist.broadcast(blk, src=src, group=crit_group)
             ev_blk[k] = ops.record(s_crit)
             if rank == rank_of(k + 1, k + 1):
                 D = cols[k + 1][:nb]
@@ -339,7 +398,7 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
         if nbelow == 0:
             return
         buf = k % 2
-        pan, Wk = pans[buf], Wks[buf]
+        pan, Wk = pans[buf], W_of(k)
         kq = k % Q
         ops.wait(s_pan, ev_done.get(k - 2))  # rows of column k carry panels <= k-2; pans[buf] is no longer read by main
         ops.wait(s_pan, ev_blk.get(k))       # W_k and the solved block (k+1, k) are in place
@@ -378,7 +437,7 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
         """Forward substitution piece (replicated) and the trailing update of the block columns > k+1."""
         nbelow = nblk - k - 1
         buf = k % 2
-        pan, Wk = pans[buf], Wks[buf]
+        pan, Wk = pans[buf], W_of(k)
         ops.wait(s_main, ev_W.get(k))
         ops.wait(s_main, ev_pan.get(k))
         with _Phase("forward_subst"):  # a_k = W_kk y_k ; y[k+1:] -= L[k+1:, k] a_k
@@ -402,6 +461,8 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
     t_issue0 = time.perf_counter()
     with ops.use(s_crit):
         ops.wait(s_crit, ev_main)
+        if p2p is not None:  # every rank has finished READING the previous call's slots before anybody overwrites them
+            p2p["W"][1].barrier(2, 30000)
         crit_step(0)
     for k in range(nblk):
         with ops.use(s_pan):

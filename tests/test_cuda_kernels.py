@@ -350,3 +350,20 @@ def test_dlpack_device_exporter_zero_copy(h):
     h.cov(OnlyDLPack(Xd), None, OnlyDLPack(thd), out=OnlyDLPack(Kd))
     assert h.sync() == 0
     np.testing.assert_array_equal(Kd.cpu().numpy(), h.cov(X, None, th))
+
+
+def test_peer_store_one_to_many(h):
+    """mfgp_peer_store: one kernel stores a block into several destination buffers (here local ones; in dist_chol.py they
+    are the peers' symmetric-memory buffers over NVLink -- covered by tests/test_multi_gpu.py on a multi-GPU box)."""
+    import torch
+
+    src = torch.randn(1024, 130, dtype=torch.float64, device="cuda")
+    dsts = [torch.zeros_like(src) for _ in range(5)]
+    h.peer_store(src, [t.data_ptr() for t in dsts], src.numel())
+    assert h.sync() == 0
+    for t in dsts:
+        assert torch.equal(t, src)
+    with pytest.raises(ValueError):
+        h.peer_store(src, [t.data_ptr() for t in dsts], src.numel() - 1)  # odd count
+    with pytest.raises(ValueError):
+        h.peer_store(src, [dsts[0].data_ptr()] * 9, src.numel())  # > MFGP_PEER_MAX destinations
