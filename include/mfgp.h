@@ -202,6 +202,11 @@ int mfgp_gemm(mfgp_handle* h, char transa, char transb, int m, int n, int k, dou
 int mfgp_potrf(mfgp_handle* h, double* A, int N, long lda);
 /* Winv [N, N] = inv(L) for the lower factor produced by mfgp_potrf. */
 int mfgp_potrf_inv(mfgp_handle* h, double* A, int N, long lda, double* Winv, long ldw);
+/* Y[M, 0:nc] += alpha * A[M, K] X[K, 0:nc] for nc <= 2 right-hand sides (device pointers; A rows 16-byte aligned, K <= 4096).
+ * The replicated forward-substitution step of the distributed Cholesky (y[k+1:] -= L[k+1:, k] a_k), HBM-bound. */
+int mfgp_tall_skinny_update(mfgp_handle* h, int M, int K, int nc, double alpha, const double* A, long lda, const double* X,
+                            long ldx, double* Y, long ldy);
+
 /* One-to-many store: `count` doubles (even, 16-byte aligned) from src into ndst <= MFGP_PEER_MAX destination buffers in ONE
  * kernel on the handle's stream.  The destinations are device pointers valid in this process -- buffers of PEER GPUs mapped
  * over NVLink (symmetric memory, CUDA IPC) or local ones.  Used for the critical-path messages of the distributed Cholesky

@@ -65,6 +65,7 @@ def _load():
         "mfgp_gemm": ([vp, C.c_char, C.c_char, i, i, i, d, vp, l, vp, l, d, vp, l], i),
         "mfgp_potrf": ([vp, vp, i, l], i),
         "mfgp_potrf_inv": ([vp, vp, i, l, vp, l], i),
+        "mfgp_tall_skinny_update": ([vp, i, i, i, d, vp, l, vp, l, vp, l], i),
         "mfgp_peer_store": ([vp, vp, l, i, C.POINTER(vp)], i),
         "mfgp_fp64_peak": ([vp, i, i, C.POINTER(d)], i),
     }
@@ -82,7 +83,7 @@ EXPORTED_SYMBOLS = [
     "mfgp_gpr_predict", "mfgp_gpr_batched_nlml_grad", "mfgp_gpr_batched_adam",
     "mfgp_graph_nparams", "mfgp_graph_cov", "mfgp_graph_cov_diag", "mfgp_graph_gpr_nlml_grad", "mfgp_svgp_elbo_grad", "mfgp_svgp_elbo_grad_v", "mfgp_svgp_predict", "mfgp_svgp_adam",
     "mfgp_svgp_flat_size", "mfgp_svgp_constrain", "mfgp_svgp_elbo_grad_flat", "mfgp_svgp_adam_update", "mfgp_gemm",
-    "mfgp_potrf", "mfgp_potrf_inv", "mfgp_peer_store", "mfgp_fp64_peak",
+    "mfgp_potrf", "mfgp_potrf_inv", "mfgp_tall_skinny_update", "mfgp_peer_store", "mfgp_fp64_peak",
 ]
 
 

@@ -508,6 +508,63 @@ int mfgp_potrf_inv(mfgp_handle* h, double* A, int N, long lda, double* Winv, lon
     return potrf_common(h, A, N, lda, Winv, ldw);
 }
 
+// ---- tall-skinny update ---------------------------------------------------------------------------------
+// Y[M, 0:nc] += alpha * A[M, K] X[K, 0:nc] for nc <= 2 right-hand sides: the forward-substitution step of the distributed
+// Cholesky (y[k+1:] -= L[k+1:, k] a_k, M up to N rows, K = block size).  HBM bound (every row of A is read once); the 64-wide
+// GEMM tiles would compute 32x more columns than exist.  One warp per row, 128-bit loads, X staged in shared memory.
+__global__ void __launch_bounds__(256) tall_skinny_kernel(int M, int K, int nc, double alpha, const double* __restrict__ A, long lda,
+                                                          const double* __restrict__ X, long ldx, double* __restrict__ Y, long ldy) {
+    extern __shared__ double xs[];  // [K][2]
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        xs[2 * i] = X[(long)i * ldx];
+        xs[2 * i + 1] = nc > 1 ? X[(long)i * ldx + 1] : 0.0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warps = (blockDim.x >> 5) * gridDim.x;
+    for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < M; r += warps) {
+        const double* row = A + (long)r * lda;
+        double s0 = 0.0, s1 = 0.0;
+        for (int k = 2 * lane; k + 1 < K; k += 64) {
+            const double2 a = *reinterpret_cast<const double2*>(row + k);
+            s0 = fma(a.x, xs[2 * k], s0);
+            s1 = fma(a.x, xs[2 * k + 1], s1);
+            s0 = fma(a.y, xs[2 * k + 2], s0);
+            s1 = fma(a.y, xs[2 * k + 3], s1);
+        }
+        if ((K & 1) && lane == 0) {
+            s0 = fma(row[K - 1], xs[2 * (K - 1)], s0);
+            s1 = fma(row[K - 1], xs[2 * (K - 1) + 1], s1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        if (lane == 0) {
+            Y[(long)r * ldy] = fma(alpha, s0, Y[(long)r * ldy]);
+            if (nc > 1) Y[(long)r * ldy + 1] = fma(alpha, s1, Y[(long)r * ldy + 1]);
+        }
+    }
+}
+
+int mfgp_tall_skinny_update(mfgp_handle* h, int M, int K, int nc, double alpha, const double* A, long lda, const double* X,
+                            long ldx, double* Y, long ldy) {
+    CHECK_H(h);
+    if (!A || !X || !Y || M < 0 || K < 1 || K > 4096 || nc < 1 || nc > 2 || lda < K || (lda & 1) || (reinterpret_cast<size_t>(A) & 15) ||
+        ldx < nc || ldy < nc)
+        return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_tall_skinny_update: bad argument (1 <= nc <= 2, K <= 4096, even lda, 16-byte aligned A)");
+    if (!mfgp_is_device_ptr(A) || !mfgp_is_device_ptr(X) || !mfgp_is_device_ptr(Y))
+        return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_tall_skinny_update: device pointers only");
+    if (M == 0) return 0;
+    cudaSetDevice(h->device);
+    long blocks = (M + 7) / 8;
+    const long cap = (long)h->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    tall_skinny_kernel<<<(unsigned)blocks, 256, (size_t)K * 16, h->stream>>>(M, K, nc, alpha, A, lda, X, ldx, Y, ldy);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
 // ---- one-to-many store over peer memory ----------------------------------------------------------------
 // The critical-path messages of the distributed Cholesky (inv(L_kk) and the early block (k+1, k), nb x nb doubles) go to
 // every other GPU of the box.  With the peers' buffers mapped into this process (symmetric memory over NVLink / NVSwitch)

@@ -45,10 +45,18 @@ __device__ __forceinline__ int tile_off(int r, int c) { return r * 8 + ((((c >> 
 
 constexpr int DT = NB / 8;                  // 16 tile rows
 constexpr int DTRI = DT * (DT + 1) / 2;     // 136 lower tiles
-constexpr int DIAG_THREADS = 128;           // 4 warps, one DMMA pipe each
+// Warps of the diagonal-block kernel.  The kernel is latency bound (ncu, round 1: one warp per scheduler issues an
+// instruction every 6 cycles; 23 % of them are address arithmetic), so more warps per scheduler shorten it directly:
+// measured (profiles/r02_potrf_diag_warps.log) with 4 / 8 / 16 warps: potrf_inv of a 1024 block 924 / 802 / 792 us, potrf
+// N = 8192 19.2 / 20.3 / 20.3 TFLOP/s, N = 16 384 29.1 / 29.5 / 29.5 (cuSOLVER 29.5).  MFGP_DIAG_WARPS overrides at build time.
+#ifndef MFGP_DIAG_WARPS
+#define MFGP_DIAG_WARPS 8
+#endif
+constexpr int DIAG_WARPS = MFGP_DIAG_WARPS;
+constexpr int DIAG_THREADS = 32 * DIAG_WARPS;
 
 // One CTA factors a 128x128 diagonal block on the FP64 tensor path and inverts the factor:
-//   left-looking over 8-wide block columns; tile rows are dealt round-robin to the 4 warps;
+//   left-looking over 8-wide block columns; tile rows are dealt round-robin to the DIAG_WARPS warps;
 //   the 8x8 diagonal tile is factored redundantly in registers by one warp (no shuffles);
 //   W = L^-1 is then built column by column (columns are independent -> no block barriers).
 __global__ void __launch_bounds__(DIAG_THREADS, 1) potrf_diag_kernel(DiagArgs p) {
@@ -144,11 +152,11 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) potrf_diag_kernel(DiagArgs p)
 #pragma unroll 1
     for (int kb = 0; kb < ntb; ++kb) {
         // ---- finish column kb: only the term k = kb-1 is still missing (earlier terms were applied one step ahead)
-        if (kb > 0) update_tiles(kb, kb - 1, kb, warp, 4);
+        if (kb > 0) update_tiles(kb, kb - 1, kb, warp, DIAG_WARPS);
         __syncthreads();
         // ---- warp 0: diagonal tile (redundant register Cholesky + inverse); warps 1-3: look-ahead on column kb+1
         if (warp != 0) {
-            if (kb + 1 < ntb && kb > 0) update_tiles(kb + 1, 0, kb, warp - 1, 3);
+            if (kb + 1 < ntb && kb > 0) update_tiles(kb + 1, 0, kb, warp - 1, DIAG_WARPS - 1);
         } else {
             double* td = Lt + tslot(kb, kb) * 64;
             double* tw = Wt + tslot(kb, kb) * 64;
@@ -202,13 +210,13 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) potrf_diag_kernel(DiagArgs p)
             }
         }
         __syncthreads();
-        // ---- panel: L_ik = A_ik inv(L_kk)^T for rows i = kb + 1 + warp + 4s -------------------------------
+        // ---- panel: L_ik = A_ik inv(L_kk)^T for rows i = kb + 1 + warp + DIAG_WARPS s ---------------------
         {
             const double* tw = Wt + tslot(kb, kb) * 64;
             const double wb0 = tw[km0], wb1 = tw[km1];
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const int i = kb + 1 + warp + 4 * s;
+            for (int s = 0; s < (DT + DIAG_WARPS - 1) / DIAG_WARPS; ++s) {
+                const int i = kb + 1 + warp + DIAG_WARPS * s;
                 if (i < ntb) {
                     double* ta = Lt + tslot(i, kb) * 64;
                     const double a0 = ta[km0], a1 = ta[km1];
@@ -232,9 +240,9 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1) potrf_diag_kernel(DiagArgs p)
     __syncthreads();
     if (tid < ntb) p.logd[bz * p.stride_logd + 8 * tid] = 0.5 * lg[tid];
 
-    // ---- W = L^-1: column block j owned by warp j % 4 (columns are independent) ---------------------------
+    // ---- W = L^-1: column block j owned by warp j % DIAG_WARPS (columns are independent) ------------------
 #pragma unroll 1
-    for (int j = warp; j < ntb; j += 4) {
+    for (int j = warp; j < ntb; j += DIAG_WARPS) {
 #pragma unroll 1
         for (int i = j + 1; i < ntb; ++i) {
             double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;  // two interleaved accumulator chains

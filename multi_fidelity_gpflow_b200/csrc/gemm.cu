@@ -74,13 +74,14 @@ __device__ __forceinline__ void tma_load(uint32_t dst, const CUtensorMap* tm, ui
                  : "memory");
 }
 
-// One stage of one operand.  K-major: a single box [ROWS][BK].  M-major: ROWS / 16 boxes [BK][16].
+// One stage of one operand, issued by the lanes of warp 0.  K-major: a single box [ROWS][BK] (lane 0).  M-major: ROWS / 16
+// boxes [BK][16], one per lane, so that the eight boxes of a 128-row operand are issued side by side, not one after another.
 template <bool KMAJOR, int ROWS>
-__device__ __forceinline__ void tma_operand(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int row0, int k0, int b1, int b2) {
-    if (KMAJOR) tma_load(dst, tm, bar, k0, row0, b1, b2);
-    else {
-#pragma unroll
-        for (int b = 0; b < ROWS / 16; ++b) tma_load(dst + b * 2048, tm, bar, row0 + 16 * b, k0, b1, b2);
+__device__ __forceinline__ void tma_operand(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int row0, int k0, int b1, int b2, int lane) {
+    if (KMAJOR) {
+        if (lane == 0) tma_load(dst, tm, bar, k0, row0, b1, b2);
+    } else {
+        if (lane < ROWS / 16) tma_load(dst + lane * 2048, tm, bar, row0 + 16 * lane, k0, b1, b2);
     }
 }
 
@@ -160,11 +161,14 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN == 128 * 
     }
     __syncthreads();
 
-    auto load_stage = [&](int stage, int k0) {  // one elected thread: arm the barrier, issue the boxes
+    // Warp 0 feeds the ring: lane 0 arms the stage's barrier with the byte count (the phase cannot complete before that
+    // arrival, whatever the order in which the copies land), then the lanes issue the boxes.
+    auto load_stage = [&](int stage, int k0) {
         const uint32_t sa = sbase + stage * STAGE_BYTES, sb = sa + A_BYTES, bar = bar0 + 8 * stage;
-        mbar_expect_tx(bar, STAGE_BYTES);
-        tma_operand<A_KM, BM>(sa, &tmA, bar, i0, k0, p.bA1 ? b1 : 0, p.bA2 ? b2 : 0);
-        tma_operand<B_KM, BN>(sb, &tmB, bar, j0, k0, p.bB1 ? b1 : 0, p.bB2 ? b2 : 0);
+        if (lane == 0) mbar_expect_tx(bar, STAGE_BYTES);
+        __syncwarp();
+        tma_operand<A_KM, BM>(sa, &tmA, bar, i0, k0, p.bA1 ? b1 : 0, p.bA2 ? b2 : 0, lane);
+        tma_operand<B_KM, BN>(sb, &tmB, bar, j0, k0, p.bB1 ? b1 : 0, p.bB2 ? b2 : 0, lane);
     };
 
     double acc[MT][NTL][2];
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN == 128 * 
 #pragma unroll
     for (int n = 0; n < NTL; ++n) bcol[n] = frag_row<B_KM>(wn0, n, g);
 
-    if (tid == 0) {
+    if (warp == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES - 1; ++s)
             if (s < nk) load_stage(s, klo + s * BK);
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (BM * BN == 128 * 
         // stage (it - 1) % STAGES was read in the previous iteration: once every warp is past this barrier it may be refilled
         __syncthreads();
         const int nxt = it + STAGES - 1;
-        if (tid == 0 && nxt < nk) load_stage(nxt % STAGES, klo + nxt * BK);
+        if (warp == 0 && nxt < nk) load_stage(nxt % STAGES, klo + nxt * BK);
         mbar_wait(bar0 + 8 * (it % STAGES), (it / STAGES) & 1);  // the TMA bytes of stage `it` have landed
         const uint32_t sa = sbase + (it % STAGES) * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll

@@ -149,6 +149,12 @@ class GpuOps:
         ptr = self._vptr
         self._chk(self.L.mfgp_potrf_inv(self.h._h, ptr(A), A.shape[0], A.stride(0), ptr(W), W.stride(0)), "potrf_inv")
 
+    def tall_skinny_update(self, m, k, alpha, A, X, Y):
+        """Y[m, :nc] += alpha * A[m, k] X[k, :nc]  (nc = X.shape[1] <= 2): one HBM-bound pass over A (mfgp_tall_skinny_update)."""
+        ptr = self._vptr
+        self._chk(self.L.mfgp_tall_skinny_update(self.h._h, m, k, X.shape[1], float(alpha), ptr(A), A.stride(0), ptr(X), X.stride(0),
+                                                 ptr(Y), Y.stride(0)), "tall_skinny_update")
+
     def gemm(self, ta, tb, m, n, k, alpha, A, B, beta, C):
         ptr = self._vptr
         self._chk(self.L.mfgp_gemm(self.h._h, b"T" if ta else b"N", b"T" if tb else b"N", m, n, k, float(alpha), ptr(A),
@@ -441,7 +447,11 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
         ops.wait(s_main, ev_W.get(k))
         ops.wait(s_main, ev_pan.get(k))
         with _Phase("forward_subst"):  # a_k = W_kk y_k ; y[k+1:] -= L[k+1:, k] a_k
-            ops.gemm(False, False, nb, 2, nb, 1.0, Wk, y[k * nb:(k + 1) * nb], 0.0, ak)
+            if hasattr(ops, "tall_skinny_update"):
+                ak.zero_()
+                ops.tall_skinny_update(nb, nb, 1.0, Wk, y[k * nb:(k + 1) * nb], ak)
+            else:
+                ops.gemm(False, False, nb, 2, nb, 1.0, Wk, y[k * nb:(k + 1) * nb], 0.0, ak)
             quad.add_((ak[:, 0] * ak[:, 0]).sum())
             if want_grad:  # keep the factor: panel k, inv(L_kk) and a_k (every rank has them anyway)
                 a_all[k * nb:(k + 1) * nb].copy_(ak)
@@ -449,7 +459,10 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
                 if nbelow:
                     cache["Lcols"][k][:nbelow * nb].copy_(pan[:nbelow * nb])
             if nbelow:
-                ops.gemm(False, False, nbelow * nb, 2, nb, -1.0, pan, ak, 1.0, y[(k + 1) * nb:])
+                if hasattr(ops, "tall_skinny_update"):
+                    ops.tall_skinny_update(nbelow * nb, nb, -1.0, pan, ak, y[(k + 1) * nb:])
+                else:
+                    ops.gemm(False, False, nbelow * nb, 2, nb, -1.0, pan, ak, 1.0, y[(k + 1) * nb:])
         with _Phase("trailing_update"):
             if nbelow > 1:
                 rows = gather_local_rows(k, pan, Rloc)

@@ -367,3 +367,23 @@ def test_peer_store_one_to_many(h):
         h.peer_store(src, [t.data_ptr() for t in dsts], src.numel() - 1)  # odd count
     with pytest.raises(ValueError):
         h.peer_store(src, [dsts[0].data_ptr()] * 9, src.numel())  # > MFGP_PEER_MAX destinations
+
+
+@pytest.mark.parametrize("M,K,nc", [(1000, 512, 2), (37, 1024, 1), (4096, 1023, 2), (5, 2, 2)])
+def test_tall_skinny_update(h, M, K, nc):
+    """mfgp_tall_skinny_update (forward-substitution step of the distributed Cholesky) against NumPy."""
+    import torch
+
+    from multi_fidelity_gpflow_b200 import _lib
+
+    rng = np.random.default_rng(M + K)
+    lda = K + (K & 1)
+    A = np.zeros((M, lda))
+    A[:, :K] = rng.standard_normal((M, K))
+    X, Y = rng.standard_normal((K, 2)), rng.standard_normal((M, 2))
+    Ad, Xd, Yd = (torch.from_numpy(a).cuda() for a in (A, X, Y))
+    rc = _lib._lib.mfgp_tall_skinny_update(h._h, M, K, nc, -0.7, _lib._ptr(Ad), lda, _lib._ptr(Xd), 2, _lib._ptr(Yd), 2)
+    assert rc == 0 and h.sync() == 0
+    ref = Y.copy()
+    ref[:, :nc] += -0.7 * A[:, :K] @ X[:, :nc]
+    np.testing.assert_allclose(Yd.cpu().numpy(), ref, rtol=1e-12, atol=1e-12)
