@@ -179,55 +179,58 @@ def dp_svgp_adam(handle_or_ops, X, Y, shape, u, mask, lr_t, beta1, beta2, eps=1e
     loss_h, kl_h, scratch = torch.zeros(nsteps, **f64), torch.zeros(nsteps, **f64), torch.zeros(2, **f64)
     if hasattr(ops, "begin"):
         ops.begin()
-    use_events = timing is not None and dev.type == "cuda"
-    timed_steps = nsteps
-    if use_events:
-        import time as _time
+    try:
+        use_events = timing is not None and dev.type == "cuda"
+        timed_steps = nsteps
+        if use_events:
+            import time as _time
 
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dist.barrier(group=group)
-        t_setup = _time.perf_counter()
-        e0.record()
-    def one_step():
-        ops.constrain(cfg, has_W, ud, c)
-        ops.elbo_grad_flat(cfg, Xd, Yd, has_W, c, world, eg)
-        if world > 1:
-            dist.all_reduce(eg, op=dist.ReduceOp.SUM, group=group)  # in place on the buffer the kernels wrote
-        ops.adam_update(cfg, has_W, ud, md, vd, mk, c, eg, lrd, step, beta1, beta2, eps, loss_h, kl_h, scratch)
-
-    if use_graph is None:
-        use_graph = dev.type == "cuda" and nsteps > 3
-    done = 0
-    if use_graph:
-        for _ in range(2):  # eager: first-call attribute opt-ins, pool growth, NCCL channel set-up
-            one_step()
-        graph = torch.cuda.CUDAGraph()
-        cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            if hasattr(ops, "h"):
-                ops.h.set_stream(side.cuda_stream)
-            with torch.cuda.graph(graph, stream=side, capture_error_mode="relaxed"):
-                one_step()  # recorded, not executed
-        cur.wait_stream(side)
-        if hasattr(ops, "h"):
-            ops.h.set_stream(cur.cuda_stream)
-        if use_events:  # steady state = the replayed steps
-            torch.cuda.current_stream().synchronize()
-            timing["setup_ms"] = (_time.perf_counter() - t_setup) * 1e3
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             dist.barrier(group=group)
+            t_setup = _time.perf_counter()
             e0.record()
-            timed_steps = nsteps - 2
-        for _ in range(2, nsteps):
-            graph.replay()
-        done = nsteps
-    for _ in range(done, nsteps):
-        one_step()
-    if use_events:
-        e1.record()
-    if hasattr(ops, "end"):
-        ops.end()
+
+        def one_step():
+            ops.constrain(cfg, has_W, ud, c)
+            ops.elbo_grad_flat(cfg, Xd, Yd, has_W, c, world, eg)
+            if world > 1:
+                dist.all_reduce(eg, op=dist.ReduceOp.SUM, group=group)  # in place on the buffer the kernels wrote
+            ops.adam_update(cfg, has_W, ud, md, vd, mk, c, eg, lrd, step, beta1, beta2, eps, loss_h, kl_h, scratch)
+
+        if use_graph is None:
+            use_graph = dev.type == "cuda" and nsteps > 3
+        done = 0
+        if use_graph:
+            for _ in range(2):  # eager: first-call attribute opt-ins, pool growth, NCCL channel set-up
+                one_step()
+            graph = torch.cuda.CUDAGraph()
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                if hasattr(ops, "h"):
+                    ops.h.set_stream(side.cuda_stream)
+                with torch.cuda.graph(graph, stream=side, capture_error_mode="relaxed"):
+                    one_step()  # recorded, not executed
+            cur.wait_stream(side)
+            if hasattr(ops, "h"):
+                ops.h.set_stream(cur.cuda_stream)
+            if use_events:  # steady state = the replayed steps
+                torch.cuda.current_stream().synchronize()
+                timing["setup_ms"] = (_time.perf_counter() - t_setup) * 1e3
+                dist.barrier(group=group)
+                e0.record()
+                timed_steps = nsteps - 2
+            for _ in range(2, nsteps):
+                graph.replay()
+            done = nsteps
+        for _ in range(done, nsteps):
+            one_step()
+        if use_events:
+            e1.record()
+    finally:  # the handle leaves async mode / the caller's stream even when a step raises
+        if hasattr(ops, "end"):
+            ops.end()
     if use_events:
         timing["ms_per_step"] = e0.elapsed_time(e1) / max(timed_steps, 1)
         timing["graph"] = bool(use_graph)
