@@ -83,10 +83,23 @@ class GpuOps:
 
         return _Ctx()
 
-    def record(self, stream):
-        ev = self.torch.cuda.Event()
+    timeline = None  # set to a dict to get a device timeline of the schedule: {label: ms since the first recorded event}
+
+    def record(self, stream, label=None):
+        timed = self.timeline is not None and label is not None
+        ev = self.torch.cuda.Event(enable_timing=timed)
         ev.record(stream)
+        if timed:
+            self.timeline.setdefault("_events", []).append((label, ev))
         return ev
+
+    def timeline_ms(self):
+        """After finish(): {label: milliseconds after the first labelled event} for one call (diagnostics only)."""
+        evs = (self.timeline or {}).pop("_events", [])
+        if not evs:
+            return {}
+        t0 = evs[0][1]
+        return {lab: t0.elapsed_time(e) for lab, e in evs}
 
     def wait(self, stream, event):
         if event is not None:
@@ -309,7 +322,7 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
             ops.cov(Xr[f * nb:len(R) * nb], Xd[j * nb:(j + 1) * nb], thd, A)
             if R[f] == j:
                 A[:nb].diagonal().add_(noise)
-    ev_main = ops.record(s_main)
+    ev_main = ops.record(s_main, "assembled") if hasattr(ops, "timeline") else ops.record(s_main)
 
     logdet = torch.zeros(1, dtype=torch.float64, device=dev)
     quad = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -358,7 +371,12 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
         (k+1, k) and finish the next diagonal block, so that potrf(k+1) never waits for the bulk of panel k."""
         buf = k % 2
         Wk, blk = W_of(k), blk_of(k)
-        ops.wait(s_crit, ev_done.get(k - 2))  # W/blk buffers free; main's updates of the blocks touched below are complete
+        # Block (k, k) has received its main-stream updates once main has finished step k-3 (panels k-2 and k-1 are applied to
+        # it by THIS stream).  With one message slot per step (peer-memory path) that is all potrf(k) has to wait for, so it
+        # overlaps main's step k-2; the two-buffer NCCL path must also wait until main's step k-2 has released W/blk[k % 2].
+        # (Device timeline, 8 GPUs, N = 32 768: waiting for done[k-2] here throttled every second potrf by 4-5 ms while main
+        # was still busy with a trailing update the diagonal block does not depend on.)
+        ops.wait(s_crit, ev_done.get(k - 3 if p2p is not None else k - 2))
         with _Phase("diag_potrf_inv"):
             if rank == rank_of(k, k):
                 A = cols[k]
@@ -372,9 +390,10 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
                     ops.peer_wait(p2p["W"][1], rank_of(k, k), 0)
             else:
                 dist.broadcast(Wk, src=rank_of(k, k), group=crit_group)
-        ev_W[k] = ops.record(s_crit)
+        ev_W[k] = ops.record(s_crit, f"W{k}") if hasattr(ops, "timeline") else ops.record(s_crit)
         if k + 1 >= nblk:
             return
+        ops.wait(s_crit, ev_done.get(k - 2))  # column k below the diagonal and block (k+1, k+1) carry main's step k-2
         with _Phase("early_block"):
             src = rank_of(k + 1, k)
             if rank == src:
@@ -389,7 +408,7 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
                     ops.peer_wait(p2p["B"][1], src, 1)
             else:
                 dist.broadcast(blk, src=src, group=crit_group)
-            ev_blk[k] = ops.record(s_crit)
+            ev_blk[k] = ops.record(s_crit, f"blk{k}") if hasattr(ops, "timeline") else ops.record(s_crit)
             if rank == rank_of(k + 1, k + 1):
                 D = cols[k + 1][:nb]
                 if k >= 1:
@@ -431,13 +450,13 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
             with _Phase("bcast_panel"):
                 dist.broadcast(buf_t, src=src, group=group)
                 pan[:nbelow * nb].view(nbelow, nb, nb)[i0 - (k + 1)::P].copy_(buf_t.view(cnt, nb, nb))
-        ev_pan[k] = ops.record(s_pan)
+        ev_pan[k] = ops.record(s_pan, f"pan{k}") if hasattr(ops, "timeline") else ops.record(s_pan)
         ops.wait(s_pan, ev_done.get(k - 1))  # main has finished applying panel k-1 to the same rows of column k+1
         with _Phase("lookahead_update"):
             if k + 1 in cols:
                 rows = gather_local_rows(k, pan, piece)  # `piece` is idle between the broadcasts of two steps
                 apply_panel(k, k + 1, pan, rows, skip_diag=True)
-        ev_la[k] = ops.record(s_pan)
+        ev_la[k] = ops.record(s_pan, f"la{k}") if hasattr(ops, "timeline") else ops.record(s_pan)
 
     def main_step(k):
         """Forward substitution piece (replicated) and the trailing update of the block columns > k+1."""
@@ -469,7 +488,7 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
                 for j in Cb:
                     if j >= k + 2:
                         apply_panel(k, j, pan, rows, skip_diag=(j == k + 2))
-        ev_done[k] = ops.record(s_main)
+        ev_done[k] = ops.record(s_main, f"done{k}") if hasattr(ops, "timeline") else ops.record(s_main)
 
     t_issue0 = time.perf_counter()
     with ops.use(s_crit):

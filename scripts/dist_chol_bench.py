@@ -33,6 +33,13 @@ for rep in range(3):
     if rank == 0:
         print(f"world={world} N={N} nbd={nbd} rep {rep}: {dt*1e3:.1f} ms  {N**3/3/dt/1e12:.2f} TFLOP/s (potrf flops)  nlml={v:.6f}  host-issue {gops.stats.get('host_issue_s', 0)*1e3:.1f} ms", flush=True)
         res = {"with_gradient": wg, "alg_tflops_nlml_grad": (N**3 + 4 * N**2) / dt / 1e12 if wg else None, "world": world, "grid": list(grid) if grid else "auto", "lookahead": la, "N": N, "nbd": nbd, "sec": dt, "potrf_tflops": N**3 / 3 / dt / 1e12, "nlml": v}
+if "timeline" in sys.argv:  # device timestamps of the schedule's events on every rank (one extra call)
+    gops.timeline = {}
+    distributed_gpr_nlml(gops, ds["X"], ds["Y"], ds["theta"], ds["noise"], nbd=nbd, grid=grid, lookahead=la)
+    tl = gops.timeline_ms()
+    gops.timeline = None
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(tl, open(f"gpurun_out/dist_chol_timeline_w{world}_N{N}_nb{nbd}_rank{rank}.json", "w"))
 if "profile" in sys.argv:
     prof = {}
     distributed_gpr_nlml(h, ds["X"], ds["Y"], ds["theta"], ds["noise"], nbd=nbd, grid=grid, lookahead=la, profile=prof)

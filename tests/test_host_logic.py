@@ -326,3 +326,18 @@ def test_multibin_host_logic_with_fake_handle():
     assert fh.calls[-1] == ("adam", (4, 9), 2, True)
     with pytest.raises(ValueError):
         MultiBinMFGP(np.zeros((65, 3)), np.zeros((65, 1)), handle=fh)  # the small-matrix kernel is N <= 64
+
+
+def test_synthetic_two_fidelity_is_the_survey_config_c5():
+    """data.synthetic_two_fidelity (what bench.py's exact-GP leg feeds the product) is SURVEY 8(d) config C5 -- the same
+    arrays as the oracle's restatement of that recipe, so bench and parity tests talk about the same problem."""
+    from multi_fidelity_gpflow_b200.data import synthetic_two_fidelity
+
+    for N in (64, 1000):
+        X, Y, theta, noise = synthetic_two_fidelity(N)
+        ds = onp.synthetic_exact_dataset(N)
+        assert np.array_equal(X, ds["X"]) and np.array_equal(Y, ds["Y"]) and np.array_equal(theta, ds["theta"]) and noise == ds["noise"]
+        assert X.shape == (N, 11) and int((X[:, -1] == 1).sum()) == N // 8
+        hf = X[X[:, -1] == 1, :-1]
+        lf = X[X[:, -1] == 0, :-1]
+        assert all(any(np.array_equal(h, l) for l in lf) for h in hf[:5])  # nested design: HF inputs are LF inputs
