@@ -202,7 +202,7 @@ int mfgp_gemm(mfgp_handle* h, char transa, char transb, int m, int n, int k, dou
 int mfgp_potrf(mfgp_handle* h, double* A, int N, long lda);
 /* Winv [N, N] = inv(L) for the lower factor produced by mfgp_potrf. */
 int mfgp_potrf_inv(mfgp_handle* h, double* A, int N, long lda, double* Winv, long ldw);
-/* Y[M, 0:nc] += alpha * A[M, K] X[K, 0:nc] for nc <= 2 right-hand sides (device pointers; A rows 16-byte aligned, K <= 4096).
+/* Y[M, 0:nc] += alpha * A[M, K] X[K, 0:nc] for nc <= 2 right-hand sides (device pointers; A rows 16-byte aligned, K <= 3072).
  * The replicated forward-substitution step of the distributed Cholesky (y[k+1:] -= L[k+1:, k] a_k), HBM-bound. */
 int mfgp_tall_skinny_update(mfgp_handle* h, int M, int K, int nc, double alpha, const double* A, long lda, const double* X,
                             long ldx, double* Y, long ldy);

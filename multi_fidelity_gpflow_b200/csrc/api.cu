@@ -550,9 +550,9 @@ __global__ void __launch_bounds__(256) tall_skinny_kernel(int M, int K, int nc, 
 int mfgp_tall_skinny_update(mfgp_handle* h, int M, int K, int nc, double alpha, const double* A, long lda, const double* X,
                             long ldx, double* Y, long ldy) {
     CHECK_H(h);
-    if (!A || !X || !Y || M < 0 || K < 1 || K > 4096 || nc < 1 || nc > 2 || lda < K || (lda & 1) || (reinterpret_cast<size_t>(A) & 15) ||
+    if (!A || !X || !Y || M < 0 || K < 1 || K > 3072 || nc < 1 || nc > 2 || lda < K || (lda & 1) || (reinterpret_cast<size_t>(A) & 15) ||
         ldx < nc || ldy < nc)
-        return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_tall_skinny_update: bad argument (1 <= nc <= 2, K <= 4096, even lda, 16-byte aligned A)");
+        return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_tall_skinny_update: bad argument (1 <= nc <= 2, K <= 3072 [X is staged in 48 KB of shared memory], even lda, 16-byte aligned A)");
     if (!mfgp_is_device_ptr(A) || !mfgp_is_device_ptr(X) || !mfgp_is_device_ptr(Y))
         return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_tall_skinny_update: device pointers only");
     if (M == 0) return 0;

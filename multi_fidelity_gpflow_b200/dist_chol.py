@@ -466,7 +466,7 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
         ops.wait(s_main, ev_W.get(k))
         ops.wait(s_main, ev_pan.get(k))
         with _Phase("forward_subst"):  # a_k = W_kk y_k ; y[k+1:] -= L[k+1:, k] a_k
-            if hasattr(ops, "tall_skinny_update"):
+            if hasattr(ops, "tall_skinny_update") and nb <= 3072:
                 ak.zero_()
                 ops.tall_skinny_update(nb, nb, 1.0, Wk, y[k * nb:(k + 1) * nb], ak)
             else:
@@ -478,7 +478,7 @@ def distributed_gpr_nlml(handle_or_ops, X, Y, theta, noise, nbd=1024, group=None
                 if nbelow:
                     cache["Lcols"][k][:nbelow * nb].copy_(pan[:nbelow * nb])
             if nbelow:
-                if hasattr(ops, "tall_skinny_update"):
+                if hasattr(ops, "tall_skinny_update") and nb <= 3072:
                     ops.tall_skinny_update(nbelow * nb, nb, -1.0, pan, ak, y[(k + 1) * nb:])
                 else:
                     ops.gemm(False, False, nbelow * nb, 2, nb, -1.0, pan, ak, 1.0, y[(k + 1) * nb:])
