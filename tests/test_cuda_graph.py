@@ -100,3 +100,33 @@ def test_graph_model_adam_follows_the_reference_loop(h):
         opt.step([u], [gu])
     np.testing.assert_allclose(mdl.loss_history, hist, rtol=1e-8)
     assert mdl.loss_history[-1] < mdl.loss_history[0]
+
+
+def test_graph_edge_cases(h):
+    """No high-fidelity rows (graph.py:69,82 skip the LF-HF / HF-HF blocks), a single point, all rows dead."""
+    rng = np.random.default_rng(3)
+    m, d = 2, 3
+    gth = onp.graph_pack([1.0, 0.8], [[0.5, 0.05], [0.07, 0.5]], [(np.full(d, 0.4), 1.0), (np.full(d, 0.5), 0.9)], (np.full(d, 0.3), 0.7))
+    X = np.hstack([rng.random((25, d)), rng.integers(0, m, size=(25, 1)).astype(float)])  # LF sources only
+    np.testing.assert_allclose(h.graph_cov(X, m, gth), onp.graph_K(X, gth, m), rtol=1e-12, atol=1e-14)
+    Y = rng.standard_normal((25, 1))
+    nlml, g = h.graph_gpr_nlml_grad(X, Y, m, gth, 1e-2)
+    lml, gr, gn = otc.graph_gpr_lml_value_and_grad(X, Y, gth, m, 1e-2)
+    assert abs(nlml + lml) < 1e-9 * abs(lml)
+    ref = -np.concatenate([gr, [gn]])
+    np.testing.assert_allclose(g, ref, rtol=1e-7, atol=1e-7 * np.abs(ref).max())
+    assert g[0] == 0.0 and g[1] == 0.0  # rho never enters without high-fidelity rows; neither does the delta kernel
+    assert np.all(g[m + m * m + 2 * (d + 1):m + m * m + 3 * (d + 1)] == 0.0)
+    # a single point
+    X1 = np.array([[0.3, 0.2, 0.9, 2.0]])
+    assert h.graph_cov(X1, m, gth).shape == (1, 1)
+    v1, _ = h.graph_gpr_nlml_grad(X1, np.array([[0.5]]), m, gth, 1e-3)
+    assert abs(v1 + otc.graph_gpr_lml_value_and_grad(X1, np.array([[0.5]]), gth, m, 1e-3)[0]) < 1e-12
+    # every row dead (fidelity not in {0, 1, 2}): K = 1e-6 I, the objective is that of white noise
+    Xd = np.hstack([rng.random((6, d)), np.full((6, 1), 5.0)])
+    K = h.graph_cov(Xd, m, gth)
+    assert np.array_equal(K, 1e-6 * np.eye(6))
+    vd, gd = h.graph_gpr_nlml_grad(Xd, np.ones((6, 1)), m, gth, 1e-3)
+    s2 = 1e-3 + 1e-6
+    assert abs(vd - (0.5 * 6 / s2 + 3 * np.log(s2) + 3 * np.log(2 * np.pi))) < 1e-9 * abs(vd)
+    assert np.all(gd[:-1] == 0.0)
