@@ -194,7 +194,8 @@ int mfgp_svgp_adam_update(mfgp_handle* h, const mfgp_svgp_cfg* cfg, int has_W, d
 
 /* ---- dense fp64 building blocks (exported for tests / bench / comparators) ------------- */
 /* C[m,n] = alpha * op(A) op(B) + beta * C, row-major; transa/transb are 'N' or 'T'.
- * Runs the DMMA (mma.sync m8n8k4 f64) tile kernel. */
+ * Runs the DMMA (mma.sync m8n8k4 f64) tile kernel; the operand tiles are fed by TMA (cp.async.bulk.tensor + mbarrier), which
+ * is why A, B must be 16-byte aligned with even lda / ldb (tensor-map strides are multiples of 16 bytes). */
 int mfgp_gemm(mfgp_handle* h, char transa, char transb, int m, int n, int k, double alpha,
               const double* A, long lda, const double* B, long ldb, double beta, double* C, long ldc);
 /* In-place lower Cholesky A = L L^T (row-major).  Only the lower triangle is referenced; on return the
