@@ -328,7 +328,8 @@ int launch_potrf(cudaStream_t s, const CholArgs& a) {
     // Look-ahead: the latency-bound chain  diag -> panel -> inner update -> diag -> panel  runs on the aux stream and
     // overlaps the FP64-bound trailing update of the previous outer step; the main stream hands over the next
     // OB columns early.
-    const bool la = a.aux != nullptr && a.ev != nullptr && N > 2 * OB;
+    static const int la_min = [] { const char* e = getenv("MFGP_POTRF_LA_MIN"); return e ? atoi(e) : 0; }();  // experiments
+    const bool la = a.aux != nullptr && a.ev != nullptr && N > 2 * OB && N > la_min;
     cudaStream_t sp = la ? a.aux : s;
     if (la) {
         cudaEventRecord(a.ev[0], s);

@@ -16,9 +16,18 @@ which = sys.argv[1] if len(sys.argv) > 1 else "single"
 mdl = SingleBinSVGP(X, Y, se(), se(), P, ps.extras["Z_kmeans300"]) if which == "single" else \
     LatentMFCoregionalizationSVGP(X, Y, se(), se(), num_latents=15, num_inducing=300, num_outputs=P)
 mdl.optimize_on_device((X, Y), max_iters=3, initial_lr=0.005)
-if which != "single":
-    mdl.loss_history, mdl.kl_history = [], []
+def timed(steps):
+    if which != "single":
+        mdl.loss_history, mdl.kl_history = [], []
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    mdl.optimize_on_device((X, Y), max_iters=steps, initial_lr=0.005)
+    return time.perf_counter() - t0
 steps = 20
-torch.cuda.synchronize(); t0 = time.perf_counter()
-mdl.optimize_on_device((X, Y), max_iters=steps, initial_lr=0.005)
-print(f"{which}: {(time.perf_counter() - t0) / steps * 1e3:.3f} ms per step  (MFGP_GEMM_CFG={os.environ.get('MFGP_GEMM_CFG')})  loss {mdl.loss_history[-1]:.6f}")
+long_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+t20 = timed(steps)
+print(f"{which}: {t20 / steps * 1e3:.3f} ms per step  (MFGP_GEMM_CFG={os.environ.get('MFGP_GEMM_CFG')})  loss {mdl.loss_history[-1]:.6f}")
+if long_steps > steps:
+    # the per-call cost (parameters + Adam moments host<->device, the eager first step, graph capture) is the same for
+    # both lengths: the difference isolates the replayed step
+    tl = timed(long_steps)
+    print(f"{which}: steady state {(tl - t20) / (long_steps - steps) * 1e3:.3f} ms per step; per-call cost {(t20 - steps * (tl - t20) / (long_steps - steps)) * 1e3:.1f} ms")
