@@ -151,6 +151,35 @@ __device__ inline void tile_dots(const double* __restrict__ A, const double* __r
     }
 }
 
+// Streaming-kernel variant: ACCUMULATES onto acc (the caller seeds it with the exponent's additive terms, which saves a
+// zero-fill and an add per element) and unrolls fully when the dimension is a compile-time constant (D > 0), so the
+// panel rows are immediate offsets of one base register instead of a loop with address arithmetic.
+template <int D>
+__device__ __forceinline__ void tile_dots_acc(const double* __restrict__ A, const double* __restrict__ B, int d, int r0, int tx,
+                                              double acc[4][4]) {
+    const double* pa = A + r0;
+    const double* pb = B + 2 * tx;
+    auto step = [&](int k) {
+        const double2 a01 = *reinterpret_cast<const double2*>(pa + k * COV_TILE);
+        const double2 a23 = *reinterpret_cast<const double2*>(pa + k * COV_TILE + 2);
+        const double2 b01 = *reinterpret_cast<const double2*>(pb + k * COV_TILE);
+        const double2 b23 = *reinterpret_cast<const double2*>(pb + k * COV_TILE + 32);
+        const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+        const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+    };
+    if constexpr (D > 0) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) step(k);
+    } else {
+#pragma unroll 2
+        for (int k = 0; k < d; ++k) step(k);
+    }
+}
+
 __device__ inline int col_of(int tx, int b) { return (b < 2 ? 0 : 32) + 2 * tx + (b & 1); }
 
 __device__ inline void tile_index(long t, int TJ, int symmetric, int& I, int& J) {
@@ -508,19 +537,22 @@ struct CovStreamArgs {
     const double* diag_add_vec;
 };
 
-__global__ void __launch_bounds__(256, 2) cov_stream_kernel(CovStreamArgs p) {
+// D: input dimension when it is one of the specialised values (5, 10), else 0 = run-time d.  SYM: lower triangle of K(X, X)
+// with optional mirroring (2 CTAs per SM: the mirror staging buffer); otherwise rectangular, 3 CTAs per SM.
+template <int D, bool SYM>
+__global__ void __launch_bounds__(256, SYM ? 2 : 3) cov_stream_kernel(CovStreamArgs p) {
     extern __shared__ __align__(16) double smem[];
-    const int d = p.d, S = 2 * d + 4, T = COV_TILE;
+    __shared__ __align__(16) double etab[512];  // static: the table's shared address is an immediate in every lookup
+    const int d = D > 0 ? D : p.d, S = 2 * d + 4, T = COV_TILE;
     const int panel = S * T;             // doubles per 64-point panel
-    double* etab = smem;                 // [64]
-    double* stage0 = smem + 64;          // stage s: [a panel | b panel]
+    double* stage0 = smem;               // stage s: [a panel | b panel]
     constexpr int MROW = 18;             // staging row stride (16 values + 2 pad: 16-byte aligned rows, fewer bank conflicts)
-    double* mstage = stage0 + 4 * panel; // [8 warps][32][MROW] transposed blocks of the mirrored tile
+    double* mstage = stage0 + 4 * panel; // SYM only: [8 warps][32][MROW] transposed blocks of the mirrored tile
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int tx = (w & 1) * 8 + (lane & 7);
     const int ty = (w >> 1) * 4 + (lane >> 3);
     const int r0 = ty * 4;
-    fexp_table_fill(etab, tid, blockDim.x);
+    fexp512_table_fill(etab, tid, blockDim.x);
 
     const long w0 = (long)blockIdx.x * p.per_cta;
     long w1 = w0 + p.per_cta;
@@ -530,7 +562,7 @@ __global__ void __launch_bounds__(256, 2) cov_stream_kernel(CovStreamArgs p) {
     // walk the tiles of this CTA in linear order (row-major; lower triangle when symmetric) without re-decoding
     auto advance = [&](int& b, int& I, int& J) {
         ++J;
-        if (p.symmetric ? (J > I) : (J == p.TJ)) {
+        if (SYM ? (J > I) : (J == p.TJ)) {
             J = 0;
             if (++I == p.TI) {
                 I = 0;
@@ -559,7 +591,7 @@ __global__ void __launch_bounds__(256, 2) cov_stream_kernel(CovStreamArgs p) {
     int b, I, J;
     {
         b = (int)(w0 / p.ntiles);
-        tile_index(w0 - (long)b * p.ntiles, p.TJ, p.symmetric, I, J);
+        tile_index(w0 - (long)b * p.ntiles, p.TJ, SYM, I, J);
     }
     issue(0, b, I, J);
     int nfla = p.fa[(long)b * p.TI + I], nflb = p.fb[(long)b * p.TJ + J];
@@ -579,7 +611,6 @@ __global__ void __launch_bounds__(256, 2) cov_stream_kernel(CovStreamArgs p) {
         const double* B = A + panel;
 
         double acc[4][4], val[4][4];
-        tile_dots(A, B, d, r0, tx, acc);
         {
             const double* hA = A + 2 * d * T;
             const double* hB = B + 2 * d * T;
@@ -589,7 +620,12 @@ __global__ void __launch_bounds__(256, 2) cov_stream_kernel(CovStreamArgs p) {
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) val[a][c] = fexp_tab(acc[a][c] + (ha[a] + hb[c]), etab);
+                for (int c = 0; c < 4; ++c) acc[a][c] = ha[a] + hb[c];  // commutative: K(X, X) stays exactly symmetric
+            tile_dots_acc<D>(A, B, d, r0, tx, acc);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) val[a][c] = fexp512(acc[a][c], etab);
         }
         if ((fla | flb) & 2) {  // some row scale differs from 1: (s_a s_b) is commutative -> K(X,X) exactly symmetric
             const double* sA = A + (2 * d + 2) * T;
@@ -600,7 +636,6 @@ __global__ void __launch_bounds__(256, 2) cov_stream_kernel(CovStreamArgs p) {
                 for (int c = 0; c < 4; ++c) val[a][c] *= sA[r0 + a] * sB[col_of(tx, c)];
         }
         if ((fla & 1) && (flb & 1)) {  // tile touches the HF x HF block: add the discrepancy GP
-            tile_dots(A + d * T, B + d * T, d, r0, tx, acc);
             const double* hA = A + (2 * d + 1) * T;
             const double* hB = B + (2 * d + 1) * T;
             const double* gA = A + (2 * d + 3) * T;
@@ -608,13 +643,16 @@ __global__ void __launch_bounds__(256, 2) cov_stream_kernel(CovStreamArgs p) {
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int cc = col_of(tx, c);
-                    if (gA[r0 + a] * gB[cc] != 0.0) val[a][c] += fexp_tab(acc[a][c] + (hA[r0 + a] + hB[cc]), etab);
-                }
+                for (int c = 0; c < 4; ++c) acc[a][c] = hA[r0 + a] + hB[col_of(tx, c)];
+            tile_dots_acc<D>(A + d * T, B + d * T, d, r0, tx, acc);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (gA[r0 + a] * gB[col_of(tx, c)] != 0.0) val[a][c] += fexp512(acc[a][c], etab);
         }
         const int i0 = I * T, j0 = J * T;
-        if (p.symmetric && I == J) {
+        if (SYM && I == J) {
             const double dg = p.diag_add_vec ? p.diag_add_vec[b] : p.diag_add;
 #pragma unroll
             for (int a = 0; a < 4; ++a)
@@ -631,7 +669,7 @@ __global__ void __launch_bounds__(256, 2) cov_stream_kernel(CovStreamArgs p) {
                 *reinterpret_cast<double2*>(dst + 32) = make_double2(val[a][2], val[a][3]);
                 dst += p.ldk;
             }
-            if (p.symmetric && p.mirror && I != J) {
+            if (SYM && p.mirror && I != J) {
                 // Mirrored tile: a direct STG of the transposed 4x4 blocks touches 8 half-filled lines per instruction and
                 // backs up the LSU.  Instead each warp transposes its 16 x 32 block through a private staging buffer and
                 // every lane hands ONE full 128-byte row to the bulk-copy engine (cp.async.bulk, asynchronous, no registers).
@@ -672,7 +710,7 @@ __global__ void __launch_bounds__(256, 2) cov_stream_kernel(CovStreamArgs p) {
                     }
                 }
             }
-            if (p.symmetric && p.mirror && I != J) {
+            if (SYM && p.mirror && I != J) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int j = j0 + col_of(tx, c);
@@ -695,7 +733,7 @@ __global__ void __launch_bounds__(256, 2) cov_stream_kernel(CovStreamArgs p) {
         J = nJ;
         stage ^= 1;
     }
-    asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // shared memory must outlive the bulk copies that read it
+    if (SYM) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // shared memory must outlive the bulk copies that read it
 }
 
 }  // namespace
@@ -728,23 +766,29 @@ static int launch_cov_stream(cudaStream_t s, const CovArgs& a, int TI, int TJ, l
     q.symmetric = a.symmetric; q.mirror = a.mirror; q.vec_ok = vec_ok;
     q.diag_add = a.diag_add; q.diag_add_vec = a.diag_add_vec;
     const int sms = mfgp_current_dev_info().sms;
-    const size_t smem = (size_t)(64 + 4 * S * T + 8 * 32 * 18) * sizeof(double);
-    static SmemOptIn optin;
-    if (!optin.ensure(cov_stream_kernel, smem)) {
-        cudaFreeAsync(ws, s);
-        return -2;
-    }
+    const bool sym = a.symmetric != 0;
+    const size_t smem = (size_t)(4 * S * T + (sym ? 8 * 32 * 18 : 0)) * sizeof(double);
+    const int slots = sym ? 2 : 3;  // resident CTAs per SM (launch bounds of the two variants)
     // contiguous chunks of tiles per CTA; measured at N = 32 768: 8 chunks per resident CTA slot / <= 64 tiles 3930 GB/s,
     // 32 / <= 16 tiles 4057 GB/s (shorter tail, better balance between the two dies)
     static const int cps = [] { const char* e = getenv("MFGP_COV_CHUNKS_PER_SLOT"); return e ? atoi(e) : 32; }();
     static const int per_max = [] { const char* e = getenv("MFGP_COV_PER_MAX"); return e ? atoi(e) : 16; }();
-    long per = (q.total + (long)sms * 2 * cps - 1) / ((long)sms * 2 * cps);
+    long per = (q.total + (long)sms * slots * cps - 1) / ((long)sms * slots * cps);
     if (per < 1) per = 1;
     if (per > per_max) per = per_max;
     q.per_cta = per;
     const long grid = (q.total + per - 1) / per;
-    cov_stream_kernel<<<(unsigned)grid, 256, smem, s>>>(q);
-    const bool ok = cudaGetLastError() == cudaSuccess;
+    bool ok = true;
+    auto go = [&](auto kernel, SmemOptIn& optin) {
+        ok = optin.ensure(kernel, smem);
+        if (ok) kernel<<<(unsigned)grid, 256, smem, s>>>(q);
+    };
+    // the reference's data sets have d = 5 (HBS2021) and d = 10 (Goku): those dimensions are compiled in
+    static SmemOptIn o5s, o5r, o10s, o10r, o0s, o0r;
+    if (a.d == 5) sym ? go(cov_stream_kernel<5, true>, o5s) : go(cov_stream_kernel<5, false>, o5r);
+    else if (a.d == 10) sym ? go(cov_stream_kernel<10, true>, o10s) : go(cov_stream_kernel<10, false>, o10r);
+    else sym ? go(cov_stream_kernel<0, true>, o0s) : go(cov_stream_kernel<0, false>, o0r);
+    ok = ok && cudaGetLastError() == cudaSuccess;
     cudaFreeAsync(ws, s);
     return ok ? 0 : -2;
 }

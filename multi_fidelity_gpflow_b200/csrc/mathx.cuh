@@ -49,6 +49,33 @@ __device__ __forceinline__ double fexp_tab(double x, const double* tab) {
     return (x < -700.0) ? 0.0 : v;
 }
 
+// ---- 512-entry variant for the streaming covariance kernel (K1), where every non-FP64 instruction counts too ----
+// exp(x) = 2^k * 2^(j/512) * e^r, n = 512 k + j = round(x * 512 / ln 2), |r| <= ln2/1024, degree-4 polynomial
+// (truncation 1.6e-18; measured against a long-double exp: < 1 ulp).  Arguments below -700 are clamped with ONE unsigned
+// integer min on the high word (negative doubles order like unsigned integers) instead of a compare and two selects on
+// the result: the value is then ~1e-304, not 0.  9 FP64-pipe + 6 integer/LDS instructions, against 11 + 9 for fexp_tab.
+// `tab` = 2^(j/512), 4 KB; declare it as a static __shared__ array so that its address is an immediate of the lookup.
+__device__ __forceinline__ void fexp512_table_fill(double* tab, int tid, int nthreads) {
+    for (int j = tid; j < 512; j += nthreads) tab[j] = exp2((double)j * (1.0 / 512.0));
+}
+__device__ __forceinline__ double fexp512(double x, const double* tab) {
+    {
+        const unsigned hi = min((unsigned)__double2hiint(x), 0xC085E000u);  // hi word of -700.0
+        x = __hiloint2double((int)hi, __double2loint(x));
+    }
+    const double t = fma(x, 738.6598609351493, 6755399441055744.0);     // 512 / ln 2, 1.5 * 2^52
+    const int n = __double2loint(t);
+    const double nf = t - 6755399441055744.0;
+    double r = fma(nf, -0.001353803086658445, x);                       // ln2/512, high part (21 trailing zero bits)
+    r = fma(nf, -3.7269822837316166e-13, r);                            // ln2/512, low part
+    const double T = tab[n & 511];
+    double q = fma(r, 4.1666666666666664e-02, 1.6666666666666666e-01);
+    q = fma(q, r, 0.5);
+    const double p = fma(q, r * r, r);
+    const double v = fma(T, p, T);
+    return __hiloint2double(__double2hiint(v) + ((n >> 9) << 20), __double2loint(v));
+}
+
 // 1/sqrt(x) for positive normal x: hardware seed (rsqrt.approx.ftz.f64, ~2^-22) + two Newton steps (8 instructions
 // against 13 for the CUDA library call, no special-case branch: x <= 0 / NaN give NaN or inf, which the caller detects).
 __device__ __forceinline__ double frsqrt(double x) {

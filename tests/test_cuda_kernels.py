@@ -308,6 +308,38 @@ def test_cov_streaming_kernel_full_size_properties(h):
     np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize("d", [5, 7, 10])
+def test_cov_streaming_kernel_vs_oracle(h, d):
+    """The streaming K1 path (taken from 1024 tiles on) element by element against the oracle: d = 5 and 10 are the compiled-in
+    dimensions, d = 7 the run-time one; ragged sizes, shuffled fidelities, rho != 1."""
+    rng = np.random.default_rng(40 + d)
+    X, X2, th = rand_X(rng, 2101, d), rand_X(rng, 2075, d), rand_theta(rng, d)
+    np.testing.assert_allclose(h.cov(X, X2, th), onp.mf_K(X, X2, th), rtol=1e-12, atol=1e-14)
+    Xs = rand_X(rng, 2950, d)
+    K = h.cov(Xs, None, th)
+    np.testing.assert_allclose(K, onp.mf_K(Xs, None, th), rtol=1e-12, atol=1e-14)
+    assert np.array_equal(K, K.T)
+
+
+def test_cov_streaming_kernel_far_points_underflow(h):
+    """Tiny length-scales: exponents far below -700 (and beyond the int32 range of the table index) must give |K| < 1e-300
+    off the diagonal, not garbage.  (The diagonal carries the cancellation error of the expanded squared distance the
+    reference uses too, eps * |x / ls|^2 in the exponent, hence the loose tolerance there.)"""
+    d = 5
+    rng = np.random.default_rng(3)
+    X, th = rand_X(rng, 2950, d), rand_theta(rng, d)
+    th[1:1 + d] = 1e-4   # kernel_L length-scales
+    th[2 + d:2 + 2 * d] = 1e-5
+    K = h.cov(X, None, th)
+    off = K[~np.eye(len(X), dtype=bool)]
+    assert np.all(np.isfinite(K)) and np.all(off >= 0.0) and off.max() < 1e-300
+    np.testing.assert_allclose(np.diag(K), onp.mf_K_diag(X, th), rtol=1e-4)
+    K2 = h.cov(X[:2101], X[100:2175], th)
+    assert np.all(np.isfinite(K2)) and np.all(K2 >= 0.0)
+    i, j = np.arange(100, 2101), np.arange(0, 2001)  # the shared points sit on this diagonal of the block
+    assert np.delete(K2.ravel(), i * K2.shape[1] + j).max() < 1e-300
+
+
 @pytest.mark.parametrize("N,d", [(53, 5), (130, 3), (700, 10)])
 def test_cov_grad_contraction_vs_autograd(h, N, d):
     """mfgp_cov_grad: sum_ij G_ij dK_ij/dtheta for a symmetric G given by its lower triangle (the backward pass of K)."""
