@@ -736,6 +736,204 @@ __global__ void __launch_bounds__(256, SYM ? 2 : 3) cov_stream_kernel(CovStreamA
     if (SYM) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // shared memory must outlive the bulk copies that read it
 }
 
+// ---------------------------------------------------------------------------------------------
+// Rectangular streaming variant on the FP64 tensor path.  The profile of the DFMA version (profiles/r02_ncu_cov_rect.md)
+// shows a kernel bound by instruction issue and the FP64 datapath together (50 warp instructions per 32 outputs, 21 of
+// them FP64), not by HBM.  DMMA does not shorten the datapath time (one m8n8k4 = 8 DFMA warp instructions of work) but it
+// needs 1/8 of the issue slots and half the shared-memory loads, and the exponent's additive terms ride along as two
+// extra k columns:   x_ij = sum_k a_ik b_jk + hA_i * 1 + 1 * hB_j   ->  K' = d + 2  (d = 10: exactly three k4 steps).
+// Warp w owns rows 16 (w >> 1) .. +16 and columns 32 (w & 1) .. +32 of the 64 x 64 tile = 2 x 4 m8n8 accumulator tiles;
+// lane (g, t) ends up with rows 8 mi + g, columns 8 ni + 2t, 2t + 1: every STG.128 writes 8 rows x 64 contiguous bytes.
+// Panel rows are padded to 68 doubles in shared memory so that the 8-byte fragment loads (address t * 68 + g) of a
+// half-warp fall into 16 different bank pairs.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_acc(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int COV_PS = 68;  // shared-memory pitch of a panel row (doubles)
+
+// acc[mi][ni][2] += sum over the d coordinate rows starting at row `c0` + the two augmented columns built from row `hrow`
+template <int D>
+__device__ __forceinline__ void tile_dmma(const double* __restrict__ Ar, const double* __restrict__ Bc, int d, int c0, int hrow,
+                                          int t, double acc[2][4][2]) {
+    // Ar = A panel + first row of this warp + g; Bc = B panel + first column of this warp + g
+    auto step = [&](int ks, bool regular) {
+        const int k = 4 * ks + t;
+        double a[2], b[4];
+        if (regular) {
+            const double* pa = Ar + (c0 + k) * COV_PS;
+            const double* pb = Bc + (c0 + k) * COV_PS;
+            a[0] = pa[0]; a[1] = pa[8];
+            b[0] = pb[0]; b[1] = pb[8]; b[2] = pb[16]; b[3] = pb[24];
+        } else {
+            // k < d: coordinate; k == d: (hA_i, 1); k == d + 1: (1, hB_j); beyond: zero padding
+            const int row = (k < d ? c0 + k : hrow) * COV_PS;
+            const bool la = k <= d, lb = k < d || k == d + 1;
+            const double ca = k == d + 1 ? 1.0 : 0.0, cb = k == d ? 1.0 : 0.0;
+            a[0] = la ? Ar[row] : ca; a[1] = la ? Ar[row + 8] : ca;
+            b[0] = lb ? Bc[row] : cb; b[1] = lb ? Bc[row + 8] : cb; b[2] = lb ? Bc[row + 16] : cb; b[3] = lb ? Bc[row + 24] : cb;
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) dmma_acc(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    };
+    if constexpr (D > 0) {
+        constexpr int KS = (D + 2 + 3) / 4;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) step(ks, 4 * ks + 3 < D);
+    } else {
+        const int KS = (d + 2 + 3) / 4;
+        for (int ks = 0; ks < KS; ++ks) step(ks, false);
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256, 3) cov_stream_rect_kernel(CovStreamArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(16) double etab[512];  // static: the table's shared address is an immediate in every lookup
+    const int d = D > 0 ? D : p.d, S = 2 * d + 4, T = COV_TILE;
+    constexpr int PS = COV_PS;
+    const int panel = S * PS;            // doubles per 64-point panel
+    double* stage0 = smem;               // stage s: [a panel | b panel]
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wr = (w >> 1) * 16, wc = (w & 1) * 32;  // first row / column of this warp inside the tile
+    fexp512_table_fill(etab, tid, blockDim.x);
+
+    const long w0 = (long)blockIdx.x * p.per_cta;
+    long w1 = w0 + p.per_cta;
+    if (w1 > p.total) w1 = p.total;
+    if (w0 >= w1) return;
+
+    auto advance = [&](int& b, int& I, int& J) {
+        if (++J == p.TJ) {
+            J = 0;
+            if (++I == p.TI) {
+                I = 0;
+                ++b;
+            }
+        }
+    };
+    // cp.async work split: thread -> (panel row k0 + 8m, 16-byte chunk o); constant across tiles
+    const int ck0 = tid >> 5, co = (tid & 31) * 2;
+    auto issue = [&](int stage, int b, int I, int J) {
+        double* sa = stage0 + (size_t)stage * 2 * panel + ck0 * PS + co;
+        double* sb = sa + panel;
+        const double* ga = p.Pa + (long)b * S * p.Napad + (long)I * T + (long)ck0 * p.Napad + co;
+        const double* gb = p.Pb + (long)b * S * p.Nbpad + (long)J * T + (long)ck0 * p.Nbpad + co;
+        for (int k = ck0; k < S; k += 8) {
+            cp_async16(sa, ga);
+            cp_async16(sb, gb);
+            sa += 8 * PS;
+            sb += 8 * PS;
+            ga += 8 * (long)p.Napad;
+            gb += 8 * (long)p.Nbpad;
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+
+    int b, I, J;
+    {
+        b = (int)(w0 / p.ntiles);
+        tile_index(w0 - (long)b * p.ntiles, p.TJ, 0, I, J);
+    }
+    issue(0, b, I, J);
+    int nfla = p.fa[(long)b * p.TI + I], nflb = p.fb[(long)b * p.TJ + J];
+    int stage = 0;
+    for (long wi = w0; wi < w1; ++wi) {
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();  // current stage landed for everyone; the other stage is no longer being read
+        const int fla = nfla, flb = nflb;
+        int nb = b, nI = I, nJ = J;
+        if (wi + 1 < w1) {
+            advance(nb, nI, nJ);
+            issue(stage ^ 1, nb, nI, nJ);
+            nfla = p.fa[(long)nb * p.TI + nI];  // consumed one tile later: the load latency is off the critical path
+            nflb = p.fb[(long)nb * p.TJ + nJ];
+        }
+        const double* A = stage0 + (size_t)stage * 2 * panel;
+        const double* B = A + panel;
+        const double* Ar = A + wr + g;
+        const double* Bc = B + wc + g;
+
+        double acc[2][4][2], val[2][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        tile_dmma<D>(Ar, Bc, d, 0, 2 * d, t, acc);
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) val[mi][ni][e] = fexp512(acc[mi][ni][e], etab);
+        // element (mi, ni, e) of this lane: row wr + 8 mi + g, column wc + 8 ni + 2 t + e
+        if ((fla | flb) & 2) {  // some row scale differs from 1
+            const double* sA = A + (2 * d + 2) * PS + wr + g;
+            const double* sB = B + (2 * d + 2) * PS + wc + 2 * t;
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) val[mi][ni][e] *= sA[8 * mi] * sB[8 * ni + e];
+        }
+        if ((fla & 1) && (flb & 1)) {  // tile touches the HF x HF block: add the discrepancy GP
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            tile_dmma<D>(Ar, Bc, d, d, 2 * d + 1, t, acc);
+            const double* gA = A + (2 * d + 3) * PS + wr + g;
+            const double* gB = B + (2 * d + 3) * PS + wc + 2 * t;
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        if (gA[8 * mi] * gB[8 * ni + e] != 0.0) val[mi][ni][e] += fexp512(acc[mi][ni][e], etab);
+        }
+        const int i0 = I * T + wr + g, j0 = J * T + wc + 2 * t;
+        double* __restrict__ K = p.K + (long)b * p.strideK;
+        if (p.vec_ok && I * T + T <= p.Na && J * T + T <= p.Nb) {  // interior tile: unguarded 128-bit stores
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+                double* dst = K + (long)(i0 + 8 * mi) * p.ldk + j0;
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+                    *reinterpret_cast<double2*>(dst + 8 * ni) = make_double2(val[mi][ni][0], val[mi][ni][1]);
+            }
+        } else {
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+                const int i = i0 + 8 * mi;
+                if (i >= p.Na) continue;
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const int j = j0 + 8 * ni;
+                    double* dst = K + (long)i * p.ldk + j;
+                    if (p.vec_ok && j + 1 < p.Nb) {
+                        *reinterpret_cast<double2*>(dst) = make_double2(val[mi][ni][0], val[mi][ni][1]);
+                    } else {
+                        if (j < p.Nb) dst[0] = val[mi][ni][0];
+                        if (j + 1 < p.Nb) dst[1] = val[mi][ni][1];
+                    }
+                }
+            }
+        }
+        b = nb;
+        I = nI;
+        J = nJ;
+        stage ^= 1;
+    }
+}
+
 }  // namespace
 
 static bool aligned16(const void* p) { return (reinterpret_cast<size_t>(p) & 15) == 0; }
@@ -767,7 +965,11 @@ static int launch_cov_stream(cudaStream_t s, const CovArgs& a, int TI, int TJ, l
     q.diag_add = a.diag_add; q.diag_add_vec = a.diag_add_vec;
     const int sms = mfgp_current_dev_info().sms;
     const bool sym = a.symmetric != 0;
-    const size_t smem = (size_t)(4 * S * T + (sym ? 8 * 32 * 18 : 0)) * sizeof(double);
+    // The tensor-path variant pays off when d + 2 fills whole k4 steps: measured at N = 32 768 (profiles/r02_cov_stream_variants.log)
+    // d = 10: 2.49 ms against 2.58 ms for the DFMA kernel; d = 5 (K' = 7 padded to 8): 2.19 against 2.08; run-time d = 7: 2.67 / 2.47.
+    static const bool rect_dmma = [] { const char* e = getenv("MFGP_COV_RECT_DMMA"); return !(e && e[0] == '0'); }();  // experiments
+    const bool dm = !sym && rect_dmma && a.d == 10;
+    const size_t smem = (size_t)(4 * S * (dm ? COV_PS : T) + (sym ? 8 * 32 * 18 : 0)) * sizeof(double);
     const int slots = sym ? 2 : 3;  // resident CTAs per SM (launch bounds of the two variants)
     // contiguous chunks of tiles per CTA; measured at N = 32 768: 8 chunks per resident CTA slot / <= 64 tiles 3930 GB/s,
     // 32 / <= 16 tiles 4057 GB/s (shorter tail, better balance between the two dies)
@@ -784,8 +986,9 @@ static int launch_cov_stream(cudaStream_t s, const CovArgs& a, int TI, int TJ, l
         if (ok) kernel<<<(unsigned)grid, 256, smem, s>>>(q);
     };
     // the reference's data sets have d = 5 (HBS2021) and d = 10 (Goku): those dimensions are compiled in
-    static SmemOptIn o5s, o5r, o10s, o10r, o0s, o0r;
-    if (a.d == 5) sym ? go(cov_stream_kernel<5, true>, o5s) : go(cov_stream_kernel<5, false>, o5r);
+    static SmemOptIn o5s, o5r, o10s, o10r, o0s, o0r, o10d;
+    if (dm) go(cov_stream_rect_kernel<10>, o10d);
+    else if (a.d == 5) sym ? go(cov_stream_kernel<5, true>, o5s) : go(cov_stream_kernel<5, false>, o5r);
     else if (a.d == 10) sym ? go(cov_stream_kernel<10, true>, o10s) : go(cov_stream_kernel<10, false>, o10r);
     else sym ? go(cov_stream_kernel<0, true>, o0s) : go(cov_stream_kernel<0, false>, o0r);
     ok = ok && cudaGetLastError() == cudaSuccess;
