@@ -791,6 +791,7 @@ __device__ __forceinline__ void tile_dmma(const double* __restrict__ Ar, const d
     }
 }
 
+// 3 CTAs per SM at 80 registers; 2 CTAs at 126 registers measured 3 % (N = 32 768) to 8 % (N = 16 384) slower.
 template <int D>
 __global__ void __launch_bounds__(256, 3) cov_stream_rect_kernel(CovStreamArgs p) {
     extern __shared__ __align__(16) double smem[];
@@ -971,6 +972,7 @@ static int launch_cov_stream(cudaStream_t s, const CovArgs& a, int TI, int TJ, l
     const bool dm = !sym && rect_dmma && a.d == 10;
     const size_t smem = (size_t)(4 * S * (dm ? COV_PS : T) + (sym ? 8 * 32 * 18 : 0)) * sizeof(double);
     const int slots = sym ? 2 : 3;  // resident CTAs per SM (launch bounds of the two variants)
+
     // contiguous chunks of tiles per CTA; measured at N = 32 768: 8 chunks per resident CTA slot / <= 64 tiles 3930 GB/s,
     // 32 / <= 16 tiles 4057 GB/s (shorter tail, better balance between the two dies)
     static const int cps = [] { const char* e = getenv("MFGP_COV_CHUNKS_PER_SLOT"); return e ? atoi(e) : 32; }();
