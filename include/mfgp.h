@@ -216,6 +216,30 @@ int mfgp_tall_skinny_update(mfgp_handle* h, int M, int K, int nc, double alpha, 
 #define MFGP_PEER_MAX 8
 int mfgp_peer_store(mfgp_handle* h, const double* src, long count, int ndst, double* const* dsts);
 
+/* Where the temporaries of the following calls on this handle come from.
+ *   MFGP_WS_POOL    (default) stream-ordered allocations from the device's default memory pool, per call;
+ *   MFGP_WS_MEASURE the same, and the library records the largest number of bytes one call takes;
+ *   MFGP_WS_FIXED   one arena of the measured size is allocated NOW (call it outside any stream capture) and every
+ *                   following call carves its temporaries out of it, starting again at its beginning (the predecessor's
+ *                   temporaries are dead in stream order: keep the calls on one stream).  A call that needs more than was
+ *                   measured takes the excess from the pool.
+ * Back to MFGP_WS_POOL releases the arena (stream-ordered).  *bytes (may be NULL) receives the measured size (MEASURE ->
+ * FIXED or POOL) or 0.  Purpose: library calls captured into a CUDA graph in FIXED mode contain NO allocation nodes, so the
+ * graph owns no memory.  Captured in POOL mode the temporaries become graph-owned memory (1.3 GB for the Goku single-bin
+ * SVGP step), which the driver keeps reserved after the graph is destroyed until mfgp_graph_mem_trim -- and once trimmed,
+ * the next capture pays for reserving it again (measured: 1.0 s instead of 0.07 s per mfgp_svgp_adam call).
+ * mfgp_svgp_adam does MEASURE (its eager first step) -> FIXED -> capture -> POOL itself; dist.py does the same around
+ * torch.cuda.graph.  Not thread safe per handle, like everything else. */
+#define MFGP_WS_POOL 0
+#define MFGP_WS_MEASURE 1
+#define MFGP_WS_FIXED 2
+int mfgp_workspace(mfgp_handle* h, int mode, long* bytes);
+
+/* Give the memory that DESTROYED CUDA graphs of the handle's device still reserve back to the driver
+ * (cudaDeviceGraphMemTrim).  Only graphs that captured library calls in MFGP_WS_POOL mode own memory (see mfgp_workspace,
+ * which avoids that at its root); call it after destroying such a graph.  Synchronises the stream. */
+int mfgp_graph_mem_trim(mfgp_handle* h);
+
 /* FP64 pipe microbenchmarks (bench.py: measured FP64 peak).  kind 0: DFMA, 1: DMMA m8n8k4, 2: both interleaved with equal
  * pipe time (tells whether the two share one datapath: same FLOP/s as either alone, or not: up to twice).
  * Returns achieved FLOP/s in *flops. */

@@ -67,6 +67,8 @@ def _load():
         "mfgp_potrf_inv": ([vp, vp, i, l, vp, l], i),
         "mfgp_tall_skinny_update": ([vp, i, i, i, d, vp, l, vp, l, vp, l], i),
         "mfgp_peer_store": ([vp, vp, l, i, C.POINTER(vp)], i),
+        "mfgp_graph_mem_trim": ([vp], i),
+        "mfgp_workspace": ([vp, i, C.POINTER(l)], i),
         "mfgp_fp64_peak": ([vp, i, i, C.POINTER(d)], i),
     }
     for name, (args, res) in sig.items():
@@ -83,7 +85,7 @@ EXPORTED_SYMBOLS = [
     "mfgp_gpr_predict", "mfgp_gpr_batched_nlml_grad", "mfgp_gpr_batched_adam",
     "mfgp_graph_nparams", "mfgp_graph_cov", "mfgp_graph_cov_diag", "mfgp_graph_gpr_nlml_grad", "mfgp_svgp_elbo_grad", "mfgp_svgp_elbo_grad_v", "mfgp_svgp_predict", "mfgp_svgp_adam",
     "mfgp_svgp_flat_size", "mfgp_svgp_constrain", "mfgp_svgp_elbo_grad_flat", "mfgp_svgp_adam_update", "mfgp_gemm",
-    "mfgp_potrf", "mfgp_potrf_inv", "mfgp_tall_skinny_update", "mfgp_peer_store", "mfgp_fp64_peak",
+    "mfgp_potrf", "mfgp_potrf_inv", "mfgp_tall_skinny_update", "mfgp_peer_store", "mfgp_graph_mem_trim", "mfgp_workspace", "mfgp_fp64_peak",
 ]
 
 
@@ -451,6 +453,18 @@ class Handle:
         """One kernel: `count` doubles from `src` into every raw device address in `dst_ptrs` (peer GPUs' mapped buffers or local)."""
         arr = (C.c_void_p * len(dst_ptrs))(*[C.c_void_p(int(p)) for p in dst_ptrs])
         self._check(_lib.mfgp_peer_store(self._h, _ptr(src), int(count), len(dst_ptrs), arr), "mfgp_peer_store")
+
+    WS_POOL, WS_MEASURE, WS_FIXED = 0, 1, 2
+
+    def workspace(self, mode: int) -> int:
+        """Source of the following calls' temporaries (include/mfgp.h: mfgp_workspace); returns the measured bytes."""
+        out = C.c_long(0)
+        self._check(_lib.mfgp_workspace(self._h, int(mode), C.byref(out)), "mfgp_workspace")
+        return int(out.value)
+
+    def graph_mem_trim(self):
+        """Return the memory that destroyed CUDA graphs still reserve on this device to the driver (see include/mfgp.h)."""
+        self._check(_lib.mfgp_graph_mem_trim(self._h), "mfgp_graph_mem_trim")
 
     def fp64_peak(self, kind: int, iters: int = 20000) -> float:
         out = C.c_double(0.0)

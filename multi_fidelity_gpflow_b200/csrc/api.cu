@@ -582,6 +582,45 @@ __global__ void __launch_bounds__(256) peer_store_kernel(const double2* __restri
     }
 }
 
+int mfgp_workspace(mfgp_handle* h, int mode, long* bytes) {
+    CHECK_H(h);
+    if (mode != MFGP_WS_POOL && mode != MFGP_WS_MEASURE && mode != MFGP_WS_FIXED)
+        return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_workspace: mode must be MFGP_WS_POOL, _MEASURE or _FIXED");
+    cudaSetDevice(h->device);
+    mfgp_ws_state& w = h->ws;
+    const long measured = w.mode == MFGP_WS_MEASURE ? (long)w.need : 0;
+    if (bytes) *bytes = measured;
+    if (w.arena) {  // leaving FIXED (or re-entering it): the arena goes back to the pool in stream order
+        CUDA_TRY(h, cudaFreeAsync(w.arena, h->stream));
+        w.arena = nullptr;
+        w.cap = w.off = 0;
+    }
+    if (mode == MFGP_WS_FIXED) {
+        if (w.mode != MFGP_WS_MEASURE) return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_workspace: MFGP_WS_FIXED follows MFGP_WS_MEASURE");
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(h->stream, &cs);
+        if (cs != cudaStreamCaptureStatusNone)
+            return mfgp_fail(h, MFGP_ERR_ARG, "mfgp_workspace: allocate the arena outside the stream capture");
+        const size_t cap = measured > 0 ? (size_t)measured : 256;
+        void* p = nullptr;
+        CUDA_TRY(h, cudaMallocAsync(&p, cap, h->stream));
+        w.arena = static_cast<char*>(p);
+        w.cap = cap;
+    }
+    w.mode = mode;
+    w.base_depth = w.depth;
+    w.cur = w.need = w.off = w.spilled = 0;
+    return 0;
+}
+
+int mfgp_graph_mem_trim(mfgp_handle* h) {
+    CHECK_H(h);
+    cudaSetDevice(h->device);
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaDeviceGraphMemTrim(h->device));
+    return 0;
+}
+
 int mfgp_peer_store(mfgp_handle* h, const double* src, long count, int ndst, double* const* dsts) {
     CHECK_H(h);
     if (!src || !dsts || count < 0 || (count & 1) || ndst < 0 || ndst > MFGP_PEER_MAX || (reinterpret_cast<size_t>(src) & 15))

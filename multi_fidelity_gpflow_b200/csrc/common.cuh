@@ -14,7 +14,46 @@
 #define MFGP_ERR_CUDA (-2)
 #define MFGP_ERR_UNSUPPORTED (-3)
 
+// Where a call's temporaries come from (mfgp_workspace in include/mfgp.h).  POOL: stream-ordered allocations from the device's
+// default memory pool.  MEASURE: the same, and the bytes of every call are summed (need = the largest call).  FIXED: bump
+// allocation from ONE arena that was allocated outside any stream capture; every call that opens at the depth where the
+// mode was entered starts again at offset 0 (its predecessor's temporaries are dead in stream order).  Captured into a
+// CUDA graph, a FIXED call contains no allocation nodes: the graph owns no memory that would outlive it.
+struct mfgp_ws_state {
+    int mode = MFGP_WS_POOL;
+    int depth = 0;       // live Scopes on this handle
+    int base_depth = 0;  // depth at which the mode was entered
+    size_t cur = 0, need = 0;
+    char* arena = nullptr;
+    size_t cap = 0, off = 0;
+    size_t spilled = 0;  // FIXED: bytes that did not fit and were served by the pool
+};
+inline thread_local mfgp_ws_state* mfgp_tl_ws = nullptr;  // workspace of the innermost live Scope of this thread
+
+inline cudaError_t mfgp_ws_malloc(void** p, size_t bytes, cudaStream_t s) {
+    mfgp_ws_state* w = mfgp_tl_ws;
+    const size_t a = (bytes + 255) & ~(size_t)255;
+    if (w && w->mode == MFGP_WS_FIXED) {
+        if (w->off + a <= w->cap) {
+            *p = w->arena + w->off;
+            w->off += a;
+            return cudaSuccess;
+        }
+        w->spilled += a;
+    } else if (w && w->mode == MFGP_WS_MEASURE) {
+        w->cur += a;
+        if (w->cur > w->need) w->need = w->cur;
+    }
+    return cudaMallocAsync(p, bytes, s);
+}
+inline cudaError_t mfgp_ws_free(void* p, cudaStream_t s) {
+    const mfgp_ws_state* w = mfgp_tl_ws;
+    if (w && w->arena && static_cast<char*>(p) >= w->arena && static_cast<char*>(p) < w->arena + w->cap) return cudaSuccess;
+    return cudaFreeAsync(p, s);
+}
+
 struct mfgp_handle {
+    mfgp_ws_state ws;
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
@@ -114,15 +153,25 @@ struct Scope {
     std::vector<Pending> outs;
     bool ok = true;
     bool host_out = false;
-    explicit Scope(mfgp_handle* hh) : h(hh) {}
-    ~Scope() {
-        for (void* p : temps) cudaFreeAsync(p, h->stream);
+    mfgp_ws_state* prev_ws;
+    explicit Scope(mfgp_handle* hh) : h(hh), prev_ws(mfgp_tl_ws) {
+        mfgp_ws_state& w = h->ws;
+        if (w.depth == w.base_depth) w.off = w.cur = 0;  // a new call at the level the workspace mode was entered
+        ++w.depth;
+        mfgp_tl_ws = &w;
     }
+    ~Scope() {
+        for (void* p : temps) mfgp_ws_free(p, h->stream);
+        --h->ws.depth;
+        mfgp_tl_ws = prev_ws;
+    }
+    Scope(const Scope&) = delete;
+    Scope& operator=(const Scope&) = delete;
     template <typename T>
     T* alloc(size_t count, bool zero = false) {
         void* p = nullptr;
         size_t bytes = (count ? count : 1) * sizeof(T);
-        if (cudaMallocAsync(&p, bytes, h->stream) != cudaSuccess) {
+        if (mfgp_ws_malloc(&p, bytes, h->stream) != cudaSuccess) {
             snprintf(h->err, sizeof(h->err), "cudaMallocAsync(%zu bytes) failed: %s", bytes,
                      cudaGetErrorString(cudaGetLastError()));
             ok = false;

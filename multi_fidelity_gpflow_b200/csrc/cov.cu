@@ -946,7 +946,7 @@ static int launch_cov_stream(cudaStream_t s, const CovArgs& a, int TI, int TJ, l
     const size_t pa = (size_t)a.batch * S * Napad, pb = same ? 0 : (size_t)a.batch * S * Nbpad;
     const size_t fbytes = (((size_t)a.batch * (TI + (same ? 0 : TJ))) + 15) & ~(size_t)15;
     double* ws = nullptr;
-    if (cudaMallocAsync(&ws, (pa + pb) * sizeof(double) + fbytes, s) != cudaSuccess) return -2;
+    if (mfgp_ws_malloc(reinterpret_cast<void**>(&ws), (pa + pb) * sizeof(double) + fbytes, s) != cudaSuccess) return -2;
     unsigned char* fl = reinterpret_cast<unsigned char*>(ws + pa + pb);
     cov_prescale_kernel<<<dim3(TI, a.batch), T, 0, s>>>(a.Xa, a.Na, Napad, a.d, a.theta, a.theta_stride, ws, fl);
     if (!same)
@@ -994,7 +994,7 @@ static int launch_cov_stream(cudaStream_t s, const CovArgs& a, int TI, int TJ, l
     else if (a.d == 10) sym ? go(cov_stream_kernel<10, true>, o10s) : go(cov_stream_kernel<10, false>, o10r);
     else sym ? go(cov_stream_kernel<0, true>, o0s) : go(cov_stream_kernel<0, false>, o0r);
     ok = ok && cudaGetLastError() == cudaSuccess;
-    cudaFreeAsync(ws, s);
+    mfgp_ws_free(ws, s);
     return ok ? 0 : -2;
 }
 

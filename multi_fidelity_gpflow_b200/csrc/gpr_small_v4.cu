@@ -713,11 +713,11 @@ int launch_v4(cudaStream_t st, const SmallArgs& a) {
     SmallArgs b = a;
     b.scratch = nullptr;
     if (a.grad) {  // one K^L slot per resident warp: <= 148 * 12 * 14 KB = 25 MB, stays in the 126 MB L2
-        if (cudaMallocAsync(&b.scratch, (size_t)grid * wpc * WarpMem<NT>::NTRI * 64 * sizeof(double), st) != cudaSuccess) return -2;
+        if (mfgp_ws_malloc(reinterpret_cast<void**>(&b.scratch), (size_t)grid * wpc * WarpMem<NT>::NTRI * 64 * sizeof(double), st) != cudaSuccess) return -2;
     }
     gpr_small_v4_kernel<NT, DS><<<grid, wpc * 32, bytes, st>>>(b, wd);
     const bool ok = cudaGetLastError() == cudaSuccess;
-    if (b.scratch) cudaFreeAsync(b.scratch, st);
+    if (b.scratch) mfgp_ws_free(b.scratch, st);
     return ok ? 0 : -2;
 }
 

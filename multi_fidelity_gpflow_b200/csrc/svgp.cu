@@ -676,6 +676,17 @@ struct FlatLayout {
     }
 };
 
+struct WorkspaceGuard {  // the loop's workspace mode ends on every exit path (mfgp_workspace, include/mfgp.h)
+    mfgp_handle* h;
+    bool mine;
+    explicit WorkspaceGuard(mfgp_handle* hh) : h(hh), mine(hh->ws.mode == MFGP_WS_POOL) {
+        if (mine) mfgp_workspace(h, MFGP_WS_MEASURE, nullptr);  // a caller-chosen mode is left alone
+    }
+    bool fix() { return mine && mfgp_workspace(h, MFGP_WS_FIXED, nullptr) == 0; }
+    ~WorkspaceGuard() {
+        if (mine) mfgp_workspace(h, MFGP_WS_POOL, nullptr);
+    }
+};
 struct AsyncGuard {  // nested library calls only enqueue; the caller's mode comes back on every exit path
     mfgp_handle* h;
     int was;
@@ -720,6 +731,7 @@ extern "C" int mfgp_svgp_adam(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const do
     const unsigned gb = (unsigned)((n + tb - 1) / tb);
     {
         AsyncGuard guard(h);  // the nested evaluations only enqueue: all their pointers are device memory
+        WorkspaceGuard wsg(h);  // step 0 measures the step's temporaries; the captured step takes them from one arena
         auto one_step = [&]() -> int {
             svgp_constrain_kernel<<<gb, tb, 0, s>>>(du, c, n, n_theta, o_lv, cfg->lik_lower);
             int r = mfgp_svgp_elbo_grad_v(h, cfg, dX, dY, c + o_Z, c, has_W ? c + o_W : nullptr, c + o_qm, c + o_qs, c + o_lv, ek,
@@ -738,6 +750,7 @@ extern "C" int mfgp_svgp_adam(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const do
         if (rc == 0 && nsteps > 2 && use_graph) {
             cudaGraph_t graph = nullptr;
             cudaGraphExec_t exec = nullptr;
+            wsg.fix();  // no allocation nodes in the graph (if the arena cannot be had the capture still works, see below)
             bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess;
             if (ok) {
                 const int r = one_step();
@@ -752,6 +765,13 @@ extern "C" int mfgp_svgp_adam(mfgp_handle* h, const mfgp_svgp_cfg* cfg, const do
             }
             if (exec) cudaGraphExecDestroy(exec);
             if (graph) cudaGraphDestroy(graph);
+            // Temporaries that did not come from the arena were captured as graph-owned allocations, which the driver keeps
+            // reserved after the graph is destroyed (include/mfgp.h: mfgp_workspace).  Hand them back once the replays
+            // have drained.
+            if ((exec || graph) && (h->ws.mode != MFGP_WS_FIXED || h->ws.spilled)) {
+                cudaStreamSynchronize(s);
+                cudaDeviceGraphMemTrim(h->device);
+            }
         }
         for (; done < nsteps && rc == 0; ++done) rc = one_step();
     }

@@ -179,6 +179,7 @@ def dp_svgp_adam(handle_or_ops, X, Y, shape, u, mask, lr_t, beta1, beta2, eps=1e
     loss_h, kl_h, scratch = torch.zeros(nsteps, **f64), torch.zeros(nsteps, **f64), torch.zeros(2, **f64)
     if hasattr(ops, "begin"):
         ops.begin()
+    graph = lib_h = None
     try:
         use_events = timing is not None and dev.type == "cuda"
         timed_steps = nsteps
@@ -201,8 +202,15 @@ def dp_svgp_adam(handle_or_ops, X, Y, shape, u, mask, lr_t, beta1, beta2, eps=1e
             use_graph = dev.type == "cuda" and nsteps > 3
         done = 0
         if use_graph:
+            lib_h = getattr(ops, "h", None)
+            if lib_h is not None:
+                lib_h.workspace(lib_h.WS_MEASURE)
             for _ in range(2):  # eager: first-call attribute opt-ins, pool growth, NCCL channel set-up
                 one_step()
+            if lib_h is not None:
+                # the captured step takes its temporaries from one arena allocated here, outside the capture: no allocation
+                # nodes in the graph, hence no graph-owned memory left behind (include/mfgp.h: mfgp_workspace)
+                lib_h.workspace(lib_h.WS_FIXED)
             graph = torch.cuda.CUDAGraph()
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
@@ -231,6 +239,12 @@ def dp_svgp_adam(handle_or_ops, X, Y, shape, u, mask, lr_t, beta1, beta2, eps=1e
     finally:  # the handle leaves async mode / the caller's stream even when a step raises
         if hasattr(ops, "end"):
             ops.end()
+        if graph is not None:
+            torch.cuda.current_stream().synchronize()
+            del graph
+        if lib_h is not None:
+            lib_h.workspace(lib_h.WS_POOL)
+            lib_h.graph_mem_trim()  # nothing to return unless a step outgrew the measured arena
     if use_events:
         timing["ms_per_step"] = e0.elapsed_time(e1) / max(timed_steps, 1)
         timing["graph"] = bool(use_graph)

@@ -401,6 +401,92 @@ def test_peer_store_one_to_many(h):
         h.peer_store(src, [dsts[0].data_ptr()] * 9, src.numel())  # > MFGP_PEER_MAX destinations
 
 
+def test_graph_mem_trim_after_captured_library_calls(h):
+    """Library calls captured into a caller's CUDA graph in pool mode allocate graph-owned memory; after the graph is
+    destroyed mfgp_graph_mem_trim returns it (include/mfgp.h).  The calls before, inside and after give the same result."""
+    import torch
+
+    from multi_fidelity_gpflow_b200 import _lib
+
+    rng = np.random.default_rng(5)
+    X, th = rand_X(rng, 2950, 5), rand_theta(rng, 5)  # 2950 points: the streaming path, which allocates a workspace
+    ref = h.cov(X, None, th)
+    dev = torch.device("cuda:0")
+    tX, tth = torch.from_numpy(X).to(dev), torch.from_numpy(th).to(dev)
+    K = torch.empty(len(X), len(X), dtype=torch.float64, device=dev)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    h.set_async(True)
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            h.set_stream(side.cuda_stream)
+            with torch.cuda.graph(g, stream=side, capture_error_mode="relaxed"):
+                assert _lib._lib.mfgp_cov(h._h, _lib._ptr(tX), len(X), None, len(X), 5, _lib._ptr(tth), _lib._ptr(K), len(X)) == 0
+        h.set_stream(None)
+        for _ in range(3):
+            K.zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(K.cpu().numpy(), ref)
+        del g
+    finally:
+        h.set_stream(None)
+        h.set_async(False)
+    h.graph_mem_trim()
+    np.testing.assert_array_equal(h.cov(X, None, th), ref)
+
+
+def test_workspace_fixed_arena(h):
+    """mfgp_workspace: MEASURE records a call's temporaries, FIXED serves them from one arena (eagerly and inside a captured
+    graph, which then has no allocation nodes), a call that outgrows the arena spills to the pool; results never change."""
+    import torch
+
+    from multi_fidelity_gpflow_b200 import _lib
+
+    rng = np.random.default_rng(6)
+    X, Xbig, th = rand_X(rng, 2950, 5), rand_X(rng, 3300, 5), rand_theta(rng, 5)
+    ref, ref_big = h.cov(X, None, th), h.cov(Xbig, None, th)
+    dev = torch.device("cuda:0")
+    tX, tXb, tth = torch.from_numpy(X).to(dev), torch.from_numpy(Xbig).to(dev), torch.from_numpy(th).to(dev)
+    K = torch.empty(len(X), len(X), dtype=torch.float64, device=dev)
+    Kb = torch.empty(len(Xbig), len(Xbig), dtype=torch.float64, device=dev)
+    call = lambda x, k: _lib._lib.mfgp_cov(h._h, _lib._ptr(x), len(x), None, len(x), 5, _lib._ptr(tth), _lib._ptr(k), len(x))
+    with pytest.raises(ValueError):
+        h.workspace(h.WS_FIXED)  # FIXED follows MEASURE
+    try:
+        assert h.workspace(h.WS_MEASURE) == 0
+        assert call(tX, K) == 0
+        need = h.workspace(h.WS_FIXED)
+        assert need >= 8 * 14 * 2950  # the prescaled panel workspace P[2d+4][Npad] at least
+        for _ in range(2):  # eager calls reuse the arena from its start
+            K.zero_()
+            assert call(tX, K) == 0 and h.sync() == 0
+            np.testing.assert_array_equal(K.cpu().numpy(), ref)
+        assert call(tXb, Kb) == 0 and h.sync() == 0  # larger than measured: the excess comes from the pool
+        np.testing.assert_array_equal(Kb.cpu().numpy(), ref_big)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        h.set_async(True)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            h.set_stream(side.cuda_stream)
+            with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                assert call(tX, K) == 0
+        h.set_stream(None)
+        for _ in range(3):
+            K.zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(K.cpu().numpy(), ref)
+        del g
+    finally:
+        h.set_stream(None)
+        h.set_async(False)
+        h.workspace(h.WS_POOL)
+    np.testing.assert_array_equal(h.cov(X, None, th), ref)
+
+
 @pytest.mark.parametrize("M,K,nc", [(1000, 512, 2), (37, 1024, 1), (4096, 1023, 2), (5, 2, 2)])
 def test_tall_skinny_update(h, M, K, nc):
     """mfgp_tall_skinny_update (forward-substitution step of the distributed Cholesky) against NumPy."""
