@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -30,7 +32,21 @@ struct mfgp_ws_state {
 };
 inline thread_local mfgp_ws_state* mfgp_tl_ws = nullptr;  // workspace of the innermost live Scope of this thread
 
+// MFGP_WS_DEBUG=1: every outermost call reports its wall time, the time spent inside the allocator and allocations slower
+// than 0.5 ms on stderr (how the pool-growth and host-noise outliers in the wall-clock bench legs were told apart).
+inline bool mfgp_ws_debug() { static const bool on = getenv("MFGP_WS_DEBUG") != nullptr; return on; }
+inline double& mfgp_dbg_malloc_ms() { static thread_local double ms = 0; return ms; }
+inline cudaError_t mfgp_ws_malloc_impl(void** p, size_t bytes, cudaStream_t s);
 inline cudaError_t mfgp_ws_malloc(void** p, size_t bytes, cudaStream_t s) {
+    if (!mfgp_ws_debug()) return mfgp_ws_malloc_impl(p, bytes, s);
+    const auto t0 = std::chrono::steady_clock::now();
+    const cudaError_t e = mfgp_ws_malloc_impl(p, bytes, s);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    mfgp_dbg_malloc_ms() += ms;
+    if (ms > 0.5) fprintf(stderr, "[mfgp ws] malloc %zu bytes took %.2f ms\n", bytes, ms);
+    return e;
+}
+inline cudaError_t mfgp_ws_malloc_impl(void** p, size_t bytes, cudaStream_t s) {
     mfgp_ws_state* w = mfgp_tl_ws;
     const size_t a = (bytes + 255) & ~(size_t)255;
     if (w && w->mode == MFGP_WS_FIXED) {
@@ -154,6 +170,7 @@ struct Scope {
     bool ok = true;
     bool host_out = false;
     mfgp_ws_state* prev_ws;
+    std::chrono::steady_clock::time_point t_open = std::chrono::steady_clock::now();
     explicit Scope(mfgp_handle* hh) : h(hh), prev_ws(mfgp_tl_ws) {
         mfgp_ws_state& w = h->ws;
         if (w.depth == w.base_depth) w.off = w.cur = 0;  // a new call at the level the workspace mode was entered
@@ -161,6 +178,11 @@ struct Scope {
         mfgp_tl_ws = &w;
     }
     ~Scope() {
+        if (mfgp_ws_debug() && h->ws.depth == 1) {
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_open).count();
+            fprintf(stderr, "[mfgp ws] call: %.2f ms wall, %.2f ms in malloc, %zu temporaries\n", ms, mfgp_dbg_malloc_ms(), temps.size());
+            mfgp_dbg_malloc_ms() = 0;
+        }
         for (void* p : temps) mfgp_ws_free(p, h->stream);
         --h->ws.depth;
         mfgp_tl_ws = prev_ws;
