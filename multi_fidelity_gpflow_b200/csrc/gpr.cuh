@@ -17,8 +17,10 @@ struct GprFactor {
     long ld, strideM;
     int Pp;
 };
-int gpr_factor_alloc(mfgp_handle* h, Scope& sc, int N, int P, int batch, GprFactor& f);
-// ... K (lower triangle valid, noise included) -> L, W = L^-1, a = W Y ...
+// want_W = false (value only): no W / G buffers (2 N^2 doubles less), and gpr_factor_from_K skips the triangular inverse.
+int gpr_factor_alloc(mfgp_handle* h, Scope& sc, int N, int P, int batch, GprFactor& f, bool want_W = true);
+// ... K (lower triangle valid, noise included) -> L, W = L^-1, a = W Y; without W: a = L^-1 Y by blocked forward
+// substitution over the 128-blocks with the diagonal-block inverses potrf leaves behind (N^2 P flops instead of N^3 / 3) ...
 int gpr_factor_from_K(mfgp_handle* h, const double* Y, long ldy, int per_batch_cols, int b_off, int ycols, int N, int P,
                       int batch, int* info_vec, GprFactor& f);
 // ... nlml = 1/2 |a|^2 + P sum log L_ii + N P / 2 log 2 pi ...

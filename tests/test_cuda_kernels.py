@@ -156,6 +156,26 @@ def test_gpr_nlml_grad_large_vs_oracle(h, N):
     assert abs(h.gpr_nlml(ds["X"], ds["Y"], ds["theta"], ds["noise"]) - nlml) < 1e-12 * abs(nlml)
 
 
+@pytest.mark.parametrize("N,P", [(300, 1), (1164, 3), (129, 64)])
+def test_gpr_value_only_path_matches_gradient_path(h, N, P):
+    """Value-only evaluations skip the triangular inverse (a = L^-1 Y by blocked forward substitution with the
+    diagonal-block inverses); the value must equal the one the NLML + gradient path computes, single and batched,
+    ragged last block and P columns included."""
+    rng = np.random.default_rng(N + P)
+    X, th = rand_X(rng, N, 4), rand_theta(rng, 4)
+    Y = rng.standard_normal((N, P))
+    v = h.gpr_nlml(X, Y, th, 1e-2)
+    vg, _ = h.gpr_nlml_grad(X, Y, th, 1e-2)
+    assert abs(v - vg) < 1e-11 * abs(vg)
+    assert abs(v + onp.gpr_lml(X, Y, th, 1e-2)) < 1e-9 * abs(v)
+    ths = np.stack([rand_theta(rng, 4) for _ in range(5)])
+    nz = np.full(5, 1e-2)
+    Yb = rng.standard_normal((N, 5))
+    vb, _ = h.gpr_batched_nlml_grad(X, Yb, ths, nz, want_grad=False)
+    vbg, _ = h.gpr_batched_nlml_grad(X, Yb, ths, nz)
+    np.testing.assert_allclose(vb, vbg, rtol=1e-11)
+
+
 def test_potrf_not_positive_definite(h):
     from multi_fidelity_gpflow_b200._lib import NotPositiveDefiniteError
 
