@@ -101,6 +101,35 @@ int gpr_factor_alloc(mfgp_handle* h, Scope& sc, int N, int P, int batch, GprFact
     return sc.ok ? 0 : MFGP_ERR_CUDA;
 }
 
+// out[batch][N, ld] (cols columns) <- L^-1 rhs, block row by block row: out_k = inv(L_kk) rhs_k with the diagonal-block
+// inverses potrf left in f.dinv, then rhs_{k+1:} -= L_{k+1:, k} out_k.  rhs is destroyed; L is read once (4.3 GB at
+// N = 32 768).  ld even, both arrays 16-byte aligned (the TMA-fed GEMM's contract).
+int gpr_forward_subst(mfgp_handle* h, const GprFactor& f, int N, int batch, double* rhs, double* out, int cols, long ld,
+                      long stride) {
+    cudaStream_t s = h->stream;
+    const long strideD = (long)chol_nblk(N) * CHOL_NB * CHOL_NB;
+    for (int k0 = 0; k0 < N; k0 += CHOL_NB) {
+        const int nb = N - k0 < CHOL_NB ? N - k0 : CHOL_NB, k1 = k0 + nb;
+        GemmArgs t;  // out_k = inv(L_kk) rhs_k
+        t.M = nb; t.N = cols; t.K = nb;
+        t.A = f.dinv + (long)(k0 / CHOL_NB) * CHOL_NB * CHOL_NB; t.lda = CHOL_NB; t.strideA = strideD;
+        t.B = rhs + (long)k0 * ld; t.ldb = ld; t.strideB = stride;
+        t.C = out + (long)k0 * ld; t.ldc = ld; t.strideC = stride;
+        t.batch = batch;
+        if (launch_gemm(s, t)) return mfgp_fail(h, MFGP_ERR_CUDA, "gemm (inv(L_kk) rhs_k) failed");
+        if (k1 >= N) break;
+        GemmArgs u;  // rhs_{k+1:} -= L_{k+1:, k} out_k
+        u.M = N - k1; u.N = cols; u.K = nb;
+        u.alpha = -1.0; u.beta = 1.0;
+        u.A = f.K + (long)k1 * f.ld + k0; u.lda = f.ld; u.strideA = f.strideM;
+        u.B = out + (long)k0 * ld; u.ldb = ld; u.strideB = stride;
+        u.C = rhs + (long)k1 * ld; u.ldc = ld; u.strideC = stride;
+        u.batch = batch;
+        if (launch_gemm(s, u)) return mfgp_fail(h, MFGP_ERR_CUDA, "gemm (forward substitution update) failed");
+    }
+    return 0;
+}
+
 // f.K holds the (lower triangle of the) noisy covariance: potrf -> W = L^-1 -> a = W Y.
 int gpr_factor_from_K(mfgp_handle* h, const double* Y, long ldy, int per_batch_cols, int b_off, int ycols, int N, int P,
                       int batch, int* info_vec, GprFactor& f) {
@@ -110,31 +139,8 @@ int gpr_factor_from_K(mfgp_handle* h, const double* Y, long ldy, int per_batch_c
     ch.dinv = f.dinv; ch.logd = f.logd; ch.d_info = h->d_info; ch.aux = h->aux_stream; ch.ev = h->ev; ch.info_vec = info_vec;
     if (launch_potrf(s, ch)) return mfgp_fail(h, MFGP_ERR_CUDA, "potrf launch failed");
     pack_rhs_kernel<<<dim3(64, batch), 256, 0, s>>>(Y, ldy, N, P, f.Pp, per_batch_cols, b_off, ycols, f.Yw);
-    if (!f.W) {
-        // Value only: a = L^-1 Yw, block row by block row.  a_k = inv(L_kk) y_k with the diagonal-block inverses of potrf,
-        // then y_{k+1:} -= L_{k+1:, k} a_k: L is read once (4.3 GB at N = 32 768), no N^3 / 3 inverse, no W and G buffers.
-        const long strideV = (long)N * f.Pp, strideD = (long)chol_nblk(N) * CHOL_NB * CHOL_NB;
-        for (int k0 = 0; k0 < N; k0 += CHOL_NB) {
-            const int nb = N - k0 < CHOL_NB ? N - k0 : CHOL_NB, k1 = k0 + nb;
-            GemmArgs t;  // a_k = inv(L_kk) y_k
-            t.M = nb; t.N = f.Pp; t.K = nb;
-            t.A = f.dinv + (long)(k0 / CHOL_NB) * CHOL_NB * CHOL_NB; t.lda = CHOL_NB; t.strideA = strideD;
-            t.B = f.Yw + (long)k0 * f.Pp; t.ldb = f.Pp; t.strideB = strideV;
-            t.C = f.a + (long)k0 * f.Pp; t.ldc = f.Pp; t.strideC = strideV;
-            t.batch = batch;
-            if (launch_gemm(s, t)) return mfgp_fail(h, MFGP_ERR_CUDA, "gemm (a_k = inv(L_kk) y_k) failed");
-            if (k1 >= N) break;
-            GemmArgs u;  // y_{k+1:} -= L_{k+1:, k} a_k
-            u.M = N - k1; u.N = f.Pp; u.K = nb;
-            u.alpha = -1.0; u.beta = 1.0;
-            u.A = f.K + (long)k1 * f.ld + k0; u.lda = f.ld; u.strideA = f.strideM;
-            u.B = f.a + (long)k0 * f.Pp; u.ldb = f.Pp; u.strideB = strideV;
-            u.C = f.Yw + (long)k1 * f.Pp; u.ldc = f.Pp; u.strideC = strideV;
-            u.batch = batch;
-            if (launch_gemm(s, u)) return mfgp_fail(h, MFGP_ERR_CUDA, "gemm (forward substitution update) failed");
-        }
-        return 0;
-    }
+    if (!f.W)  // value only: a = L^-1 Yw without the N^3 / 3 inverse and without the W and G buffers
+        return gpr_forward_subst(h, f, N, batch, f.Yw, f.a, f.Pp, f.Pp, (long)N * f.Pp);
     if (launch_trtri(s, ch, f.W, f.ld, f.strideM, f.G)) return mfgp_fail(h, MFGP_ERR_CUDA, "trtri launch failed");
 
     GemmArgs g;  // a = W Yw
@@ -224,7 +230,11 @@ int gpr_predict_device(mfgp_handle* h, Scope& sc, const double* X, const double*
                        double* var_d) {
     cudaStream_t s = h->stream;
     Factor f;
-    MFGP_TRY(factor(h, sc, X, Y, P, 0, 0, 0, N, d, P, 1, theta_d, noise_d, nullptr, f));
+    // A_s = L^-1 K_s by forward substitution (N^2 Ns flops in k = 128 updates) beats building W = L^-1 first (N^3 / 3 more
+    // flops) for as long as Ns < N: measured at N = 16 384 (scripts/predict_once.py) 61 + 0.0098 Ns ms against
+    // 100 + 0.0077 Ns ms for W + one full-rate GEMM.
+    const bool want_W = Ns > N;
+    MFGP_TRY(factor(h, sc, X, Y, P, 0, 0, 0, N, d, P, 1, theta_d, noise_d, nullptr, f, want_W));
     const long lds = round_up(Ns, 2);
     double* Ks = sc.alloc<double>((size_t)N * lds);
     double* As = sc.alloc<double>((size_t)N * lds);
@@ -237,14 +247,18 @@ int gpr_predict_device(mfgp_handle* h, Scope& sc, const double* X, const double*
     c.batch = 1;
     if (launch_cov(s, c)) return mfgp_fail(h, MFGP_ERR_CUDA, "cov launch failed");
     if (launch_cov_diag(s, Xs, Ns, d, theta_d, 0, kss, 0, 1)) return mfgp_fail(h, MFGP_ERR_CUDA, "cov_diag failed");
-    GemmArgs g;  // As = W Ks
-    g.transA = false; g.transB = false;
-    g.M = N; g.N = Ns; g.K = N;
-    g.A = f.W; g.lda = f.ld;
-    g.B = Ks; g.ldb = lds;
-    g.C = As; g.ldc = lds;
-    g.krange = KR_HI_I;
-    if (launch_gemm(s, g)) return mfgp_fail(h, MFGP_ERR_CUDA, "gemm (As) failed");
+    if (want_W) {
+        GemmArgs g;  // As = W Ks
+        g.transA = false; g.transB = false;
+        g.M = N; g.N = Ns; g.K = N;
+        g.A = f.W; g.lda = f.ld;
+        g.B = Ks; g.ldb = lds;
+        g.C = As; g.ldc = lds;
+        g.krange = KR_HI_I;
+        if (launch_gemm(s, g)) return mfgp_fail(h, MFGP_ERR_CUDA, "gemm (As) failed");
+    } else {
+        MFGP_TRY(gpr_forward_subst(h, f, N, 1, Ks, As, Ns, lds, 0));
+    }
     predict_var_kernel<<<(Ns + 127) / 128, 128, 0, s>>>(As, N, Ns, lds, kss, var_d);
     GemmArgs m;  // mean = As^T a
     m.transA = true; m.transB = false;

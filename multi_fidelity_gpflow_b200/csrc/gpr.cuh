@@ -23,6 +23,9 @@ int gpr_factor_alloc(mfgp_handle* h, Scope& sc, int N, int P, int batch, GprFact
 // substitution over the 128-blocks with the diagonal-block inverses potrf leaves behind (N^2 P flops instead of N^3 / 3) ...
 int gpr_factor_from_K(mfgp_handle* h, const double* Y, long ldy, int per_batch_cols, int b_off, int ycols, int N, int P,
                       int batch, int* info_vec, GprFactor& f);
+// out <- L^-1 rhs (rhs destroyed) by blocked forward substitution; see gpr.cu.
+int gpr_forward_subst(mfgp_handle* h, const GprFactor& f, int N, int batch, double* rhs, double* out, int cols, long ld,
+                      long stride);
 // ... nlml = 1/2 |a|^2 + P sum log L_ii + N P / 2 log 2 pi ...
 void gpr_nlml_from_factor(mfgp_handle* h, const GprFactor& f, int N, int P, int batch, double* nlml_d);
 // ... and f.G (lower tiles) <- alpha alpha^T - P K^-1.

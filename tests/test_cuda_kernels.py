@@ -226,6 +226,19 @@ def test_gpr_predict_vs_oracle(h):
         np.testing.assert_allclose(var, rv, rtol=1e-8, atol=1e-8 * np.abs(rv).max())
 
 
+@pytest.mark.parametrize("Ns", [3, 400, 1700])
+def test_gpr_predict_both_solve_paths(h, Ns):
+    """N = 1500: up to N test points go through the forward substitution A_s = L^-1 K_s, more through W = L^-1 and a
+    GEMM; both against the oracle (north-star tolerance 1e-8), P = 2 output columns, ragged last block."""
+    rng = np.random.default_rng(Ns)
+    X, Xs, th = rand_X(rng, 1500, 3), rand_X(rng, Ns, 3), rand_theta(rng, 3)
+    Y = rng.standard_normal((1500, 2))
+    mean, var = h.gpr_predict(X, Y, Xs, th, 1e-2)
+    rm, rv = onp.gpr_predict(X, Y, Xs, th, 1e-2)
+    np.testing.assert_allclose(mean, rm, rtol=1e-8, atol=1e-8 * np.abs(rm).max())
+    np.testing.assert_allclose(var, rv, rtol=1e-8, atol=1e-8 * np.abs(rv).max())
+
+
 # ------------------------------------------------------------------------------------ batched per-bin
 def test_batched_small_hbs_vs_oracle(h):
     ds = onp.load_dataset("hbs")
