@@ -412,7 +412,9 @@ def leg_exact_gp(cx, peak):
 
     single = single_g = None
     if cx.rank == 0:  # the single-GPU answer: the measurement at world 1, the in-run reference at world > 1
-        h.gpr_nlml(X, Y, theta, noise)  # warm-up at full size: the stream-ordered pool grows to its 17 GB working set once
+        # warm-up at full size, WITH the gradient: the stream-ordered pool grows to the 26 GB working set (K, W, G) once; the
+        # value-only call needs K alone
+        h.gpr_nlml_grad(X, Y, theta, noise)
         t0 = time.perf_counter()
         single = h.gpr_nlml(X, Y, theta, noise)
         t1 = time.perf_counter()
