@@ -682,7 +682,13 @@ struct WorkspaceGuard {  // the loop's workspace mode ends on every exit path (m
     explicit WorkspaceGuard(mfgp_handle* hh) : h(hh), mine(hh->ws.mode == MFGP_WS_POOL) {
         if (mine) mfgp_workspace(h, MFGP_WS_MEASURE, nullptr);  // a caller-chosen mode is left alone
     }
-    bool fix() { return mine && mfgp_workspace(h, MFGP_WS_FIXED, nullptr) == 0; }
+    bool fix() {
+        if (!mine) return false;
+        if (mfgp_workspace(h, MFGP_WS_FIXED, nullptr) == 0) return true;
+        cudaGetLastError();  // no arena (out of memory): the loop goes on with pool allocations, the error must not stick
+        h->err[0] = 0;
+        return false;
+    }
     ~WorkspaceGuard() {
         if (mine) mfgp_workspace(h, MFGP_WS_POOL, nullptr);
     }
