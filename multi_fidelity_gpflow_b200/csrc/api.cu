@@ -61,6 +61,7 @@ int mfgp_destroy(mfgp_handle* h) {
     CHECK_H(h);
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->ws.arena) cudaFree(h->ws.arena);  // a workspace arena left behind by a caller that never went back to MFGP_WS_POOL
     for (auto& e : h->ev) cudaEventDestroy(e);
     cudaStreamDestroy(h->own_stream);
     cudaStreamDestroy(h->aux_stream);
